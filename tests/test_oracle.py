@@ -1,0 +1,146 @@
+"""Pin the oracle (CPU restatement) against vectors produced by executing the reference
+(tests/golden/make_golden.py) and against OpenCV for the histogram definition."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import histogram as H
+from oracle import metrics as M
+from oracle import search as S
+
+DIMS = (1, 3, 7, 64, 512, 2048)
+PARAMS = {"w_angle": 1.0, "w_l1": 1.0, "w_l2": 1.0, "w_inf": 0.0, "w_mag": 0.5}
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "metrics_golden.npz"))
+
+
+@pytest.mark.parametrize("D", DIMS)
+def test_scalar_restatement_bit_exact(gold, D):
+    Q, X = gold[f"Q_{D}"], gold[f"X_{D}"]
+    table = {"cosine_similarity": M.cosine_similarity, "cosine_distance": M.cosine_distance,
+             "angular_distance": M.angular_distance, "l1_distance": M.l1_distance,
+             "l2_distance": M.l2_distance, "linf_distance": M.linf_distance,
+             "magnitude_difference": M.magnitude_difference}
+    for name, fn in table.items():
+        got = np.array([[fn(q, x) for x in X] for q in Q], dtype=np.float64)
+        assert np.array_equal(got, gold[f"{name}_{D}"]), name
+    got = np.array([[M.optimized_similarity(q, x, PARAMS) for x in X] for q in Q], dtype=np.float64)
+    assert np.array_equal(got, gold[f"optimized_similarity_{D}"])
+    got = np.array([[M.optimized_similarity(q, x, {}) for x in X] for q in Q], dtype=np.float64)
+    assert np.array_equal(got, gold[f"optimized_default_{D}"])
+    got = np.array([[M.l1_distance(q, x, normalized=False) for x in X] for q in Q], dtype=np.float64)
+    assert np.array_equal(got, gold[f"l1_raw_{D}"])
+    got = np.array([[M.l2_distance(q, x, normalized=False) for x in X] for q in Q], dtype=np.float64)
+    assert np.array_equal(got, gold[f"l2_raw_{D}"])
+
+
+def test_types_and_edge_values(gold):
+    Q, X = gold["Q_512"], gold["X_512"]
+    assert isinstance(M.cosine_similarity(Q[0], X[0]), float) and M.cosine_similarity(Q[0], X[0]) == 0.0
+    assert M.angular_distance(Q[0], X[0]) == np.pi / 2
+    assert type(M.l2_distance(Q[0], X[5])) is np.float64          # fp32 / sqrt(int) promotes
+    assert type(M.l1_distance(Q[0], X[5])) is np.float32
+    assert M.l1_distance(Q[0], X[1]) == 0 and M.linf_distance(Q[0], X[1]) == 0
+    assert np.array_equal(np.array(M.create_parameter_grid(5)["w_l1"]), gold["grid5"])
+    d = M.get_all_metrics(Q[1], X[6])
+    assert list(d) == ["cosine_similarity", "cosine_distance", "angular_distance", "l1_distance",
+                       "l2_distance", "linf_distance", "magnitude_difference"]
+
+
+@pytest.mark.parametrize("D", DIMS)
+def test_batched_matches_reference(gold, D):
+    Q, X = gold[f"Q_{D}"], gold[f"X_{D}"]
+    # fp32 batched: bit-exact where NumPy's row reduction == 1-D reduction
+    assert np.array_equal(M.pairwise(Q, X, "l1", np.float32).astype(np.float64), gold[f"l1_distance_{D}"])
+    assert np.array_equal(M.pairwise(Q, X, "linf", np.float32).astype(np.float64), gold[f"linf_distance_{D}"])
+    # fp64 "truth" vs the reference's fp32 arithmetic: fp32 rounding only
+    for name, key, atol in (("l1", "l1_distance", 0), ("l2", "l2_distance", 0), ("linf", "linf_distance", 0),
+                            ("cosine_similarity", "cosine_similarity", 2e-6),
+                            ("cosine_distance", "cosine_distance", 2e-6),
+                            ("magnitude_difference", "magnitude_difference", 1e-5)):
+        t = M.pairwise_f64(Q, X, name)
+        np.testing.assert_allclose(gold[f"{key}_{D}"], t, rtol=2e-5, atol=atol + 1e-30, err_msg=name)
+    t = M.pairwise_f64(Q, X, "angular_distance")
+    np.testing.assert_allclose(gold[f"angular_distance_{D}"], t, rtol=1e-5, atol=1e-3)   # arccos near 0/pi
+    t = M.pairwise_f64(Q, X, "optimized_similarity", params=PARAMS)
+    np.testing.assert_allclose(gold[f"optimized_similarity_{D}"], t, rtol=1e-4, atol=1e-5)
+
+
+def test_bf16_round():
+    import torch
+    x = np.random.default_rng(0).standard_normal(4096).astype(np.float32)
+    assert np.array_equal(M.bf16_round(x), torch.from_numpy(x).bfloat16().float().numpy())
+
+
+def test_search_semantics(golden_dir):
+    g = np.load(os.path.join(golden_dir, "search_golden.npz"))
+    X, Q = g["X"], g["Q"]
+    emb = {f"img_{i:04d}.jpg": X[i] for i in range(len(X))}
+    for qi, q in enumerate(Q):
+        res = S.search_images(emb, q, top_k=10)
+        assert [int(r["path"][4:8]) for r in res] == list(g[f"search_images_idx_{qi}"])
+        assert np.array_equal(np.array([r["score"] for r in res], dtype=np.float64), g[f"search_images_score_{qi}"])
+        multi = S.search_with_multiple_metrics(emb, q, top_k=5)
+        for name in ("cosine_similarity", "l1_distance", "l2_distance"):
+            assert [int(r["path"][4:8]) for r in multi[name]] == list(g[f"multi_{name}_idx_{qi}"])
+        # batched stable top-k == list.sort + slice (ties -> lower index)
+        for name, mname in (("l1_distance", "l1"), ("l2_distance", "l2"), ("linf_distance", "linf"),
+                            ("cosine_similarity", "cosine_similarity")):
+            v, i = S.topk_search(q[None], X, mname, 5, dtype=np.float32)
+            assert list(i[0]) == list(g[f"multi_{name}_idx_{qi}"]), name
+    # duplicates 5, 17, 200 of the scaled query 0 -> tie order 5, 17, 200
+    assert list(g["multi_l1_distance_idx_0"][:0]) == []
+    v, i = S.topk_search(Q[0][None], X, "cosine_similarity", 3)
+    assert set(i[0]) == {5, 17, 200}
+    assert S.search_images({}, Q[0]) == []
+
+
+def test_topk_ties_and_merge():
+    s = np.array([[1.0, 2.0, 2.0, 1.0]])
+    assert list(S.topk(s, 4, True)[1][0]) == [1, 2, 0, 3]
+    assert list(S.topk(s, 4, False)[1][0]) == [0, 3, 1, 2]
+    assert S.topk(s, 10, False)[1].shape == (1, 4)
+    rng = np.random.default_rng(3)
+    sc = rng.integers(0, 5, size=(4, 64)).astype(np.float32)
+    for desc in (False, True):
+        fv, fi = S.topk(sc, 7, desc)
+        parts_v, parts_i = [], []
+        for r in range(4):
+            v, i = S.topk(sc[:, r * 16:(r + 1) * 16], 7, desc)
+            parts_v.append(v)
+            parts_i.append(i + r * 16)
+        mv, mi = S.merge_topk(np.stack(parts_v), np.stack(parts_i), 7, desc)
+        assert np.array_equal(mi, fi) and np.array_equal(mv, fv)
+
+
+def test_hsv_restatement_all_colours():
+    import cv2
+    r, g, b = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8),
+                          np.arange(0, 256, 1, dtype=np.uint8), indexing="ij")
+    rgb = np.stack([r, g, b], -1).reshape(4096, 4096, 3)
+    ref = cv2.cvtColor(rgb, cv2.COLOR_RGB2HSV)
+    assert np.array_equal(H.rgb_to_hsv_u8(rgb), ref)
+
+
+def test_histogram_vs_opencv(golden_dir):
+    g = np.load(os.path.join(golden_dir, "hist_golden.npz"))
+    imgs = g["images"]
+    assert np.array_equal(H.histogram(imgs, "rgb"), g["rgb"])
+    assert np.array_equal(H.histogram(imgs, "hsv"), g["hsv"])
+    for im in imgs[:3]:
+        assert np.array_equal(H.histogram_cv2(im, "rgb").astype(np.uint32), H.histogram(im, "rgb")[0])
+        assert np.array_equal(H.histogram_cv2(im, "hsv").astype(np.uint32), H.histogram(im, "hsv")[0])
+    assert H.histogram(imgs, "rgb").sum(1).tolist() == [32 * 48] * len(imgs)
+    # every H value 0..179 lands in the same bin as calcHist's float LUT
+    import cv2
+    hv = np.zeros((1, 180, 3), np.uint8)
+    hv[0, :, 0] = np.arange(180)
+    ref = cv2.calcHist([hv], [0], None, [8], [0, 180]).reshape(-1)
+    mine = np.bincount(np.arange(180) * 8 // 180, minlength=8)
+    assert np.array_equal(ref.astype(np.int64), mine)
+    unit, mag = H.embedding(imgs[:2])
+    np.testing.assert_allclose(np.linalg.norm(unit, axis=1), 1.0, rtol=1e-6)
