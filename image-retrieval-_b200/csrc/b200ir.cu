@@ -1,0 +1,198 @@
+// C ABI of the retrieval hot path (declared in include/b200ir.h).  Argument validation, path
+// selection and kernel launches only: all arithmetic lives in the .cuh kernels.
+#include "common.cuh"
+#include "scan_plan.h"
+#include "select.cuh"
+#include "histogram.cuh"
+#include "gemm_topk.h"
+
+using namespace b200ir;
+
+namespace {
+
+inline bool valid_metric(int m) { return m >= 0 && m < B200IR_NUM_METRICS; }
+inline bool valid_dtype(int d) { return d == B200IR_F32 || d == B200IR_BF16; }
+inline int elem_size(int d) { return d == B200IR_F32 ? 4 : 2; }
+
+MetricParams make_params(int metric, int flags, int D, const float* w) {
+  MetricParams mp{};
+  mp.metric = metric; mp.flags = flags; mp.D = D;
+  mp.w[0] = 1.f; mp.w[1] = mp.w[2] = mp.w[3] = mp.w[4] = 0.f;      // geometric_metrics.py:78-82 defaults
+  if (w && metric == B200IR_OPTIMIZED) for (int i = 0; i < 5; ++i) mp.w[i] = w[i];
+  return mp;
+}
+
+__global__ void fill_empty_topk_kernel(float* score, int64_t* idx, int64_t n, float v) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) { score[i] = v; idx[i] = -1; }
+}
+
+template <typename T>
+__global__ void row_sqnorms_kernel(const T* __restrict__ X, int64_t N, int D, float* __restrict__ out) {
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const T* x = X + row * D;
+  float ss = 0.f;
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    const int d = d0 + lane;
+    const float v = d < D ? to_f32<T>(x[d]) : 0.f;
+    float p = v * v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    ss += p;
+  }
+  if (lane == 0) out[row] = ss;
+}
+
+bool use_tensor_path(int metric, int dtype, int64_t nq, int64_t N, int D, int k, int flags) {
+  if (flags & B200IR_FLAG_NO_TENSOR) return false;
+  return gemm_path_supported(metric, dtype, nq, N, D, k, flags);
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200ir_version(void) { return B200IR_VERSION; }
+
+const char* b200ir_error_string(int status) {
+  switch (status) {
+    case 0: return "ok";
+    case B200IR_E_ARG: return "b200ir: invalid argument (null pointer, negative size or unknown enum)";
+    case B200IR_E_K: return "b200ir: k out of range (1..256)";
+    case B200IR_E_WORKSPACE: return "b200ir: workspace missing or too small";
+    case B200IR_E_ALIGN: return "b200ir: pointer not aligned for its element type";
+    case B200IR_E_DEVICE: return "b200ir: device is not an sm_100 (B200) GPU";
+    case B200IR_E_SHAPE: return "b200ir: shape not supported";
+    default: break;
+  }
+  if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
+  return "b200ir: unknown error";
+}
+
+int b200ir_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int b200ir_row_sqnorms(const void* X, int dtype, int64_t N, int D, float* out, void* stream) {
+  if (!valid_dtype(dtype) || N < 0 || D <= 0) return B200IR_E_ARG;
+  if (N == 0) return 0;
+  if (!X || !out) return B200IR_E_ARG;
+  if (reinterpret_cast<uintptr_t>(X) % elem_size(dtype)) return B200IR_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = int(ceil_div64(N, 8));
+  if (dtype == B200IR_F32) row_sqnorms_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(X), N, D, out);
+  else row_sqnorms_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(X), N, D, out);
+  return int(cudaGetLastError());
+}
+
+size_t b200ir_topk_workspace_bytes(int metric, int dtype, int64_t nq, int64_t N, int D, int k, int flags) {
+  if (!valid_metric(metric) || !valid_dtype(dtype) || nq <= 0 || N <= 0 || D <= 0 || k < 1 || k > B200IR_MAX_K) return 0;
+  if (use_tensor_path(metric, dtype, nq, N, D, k, flags)) return gemm_workspace_bytes(metric, nq, N, D, k, flags);
+  return make_scan_plan(metric, dtype, nq, N, D, k, false).total_bytes;
+}
+
+int b200ir_topk(int metric, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D,
+                int k, int64_t index_offset, int flags, const float* weights_host,
+                float* out_score, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!valid_metric(metric) || !valid_dtype(dtype) || nq < 0 || N < 0 || D <= 0) return B200IR_E_ARG;
+  if (k < 1 || k > B200IR_MAX_K) return B200IR_E_K;
+  if (N >= (int64_t(1) << 32)) return B200IR_E_SHAPE;      // shard-local ids are 32-bit inside the keys
+  if (nq == 0) return 0;
+  if (!Q || !out_score || !out_idx || (N > 0 && !X)) return B200IR_E_ARG;
+  if (reinterpret_cast<uintptr_t>(Q) % elem_size(dtype) || reinterpret_cast<uintptr_t>(X) % elem_size(dtype)) return B200IR_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N == 0) {   // empty store: every slot is padding (app_pipeline.py:147-149 returns [])
+    const int64_t n = nq * k;
+    fill_empty_topk_kernel<<<int(ceil_div64(n, 256)), 256, 0, st>>>(out_score, out_idx, n, metric_descending(metric) ? -INFINITY : INFINITY);
+    return int(cudaGetLastError());
+  }
+  const size_t need = b200ir_topk_workspace_bytes(metric, dtype, nq, N, D, k, flags);
+  if (!workspace || workspace_bytes < need) return B200IR_E_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return B200IR_E_ALIGN;
+  const MetricParams mp = make_params(metric, flags, D, weights_host);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+
+  if (use_tensor_path(metric, dtype, nq, N, D, k, flags)) {
+    return run_gemm_topk(metric, Q, nq, X, N, D, k, index_offset, flags, mp, out_score, out_idx, ws, st);
+  }
+  const ScanPlan pl = make_scan_plan(metric, dtype, nq, N, D, k, false);
+  cudaError_t e = run_scan(pl, dtype, Q, nq, X, N, D, k, mp, ws, nullptr, st);
+  if (e != cudaSuccess) return int(e);
+  e = launch_finalize(reinterpret_cast<const uint64_t*>(ws + pl.off_partial), nq, int64_t(pl.P) * k, k, mp,
+                      index_offset, out_score, out_idx, st);
+  return int(e);
+}
+
+size_t b200ir_pairwise_workspace_bytes(int metric, int dtype, int64_t nq, int64_t N, int D) {
+  if (!valid_metric(metric) || !valid_dtype(dtype) || nq <= 0 || N <= 0 || D <= 0) return 0;
+  return make_scan_plan(metric, dtype, nq, N, D, 1, true).total_bytes;
+}
+
+int b200ir_pairwise(int metric, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D,
+                    int flags, const float* weights_host, float* out, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  if (!valid_metric(metric) || !valid_dtype(dtype) || nq < 0 || N < 0 || D <= 0) return B200IR_E_ARG;
+  if (N >= (int64_t(1) << 32)) return B200IR_E_SHAPE;
+  if (nq == 0 || N == 0) return 0;
+  if (!Q || !X || !out) return B200IR_E_ARG;
+  if (reinterpret_cast<uintptr_t>(Q) % elem_size(dtype) || reinterpret_cast<uintptr_t>(X) % elem_size(dtype)) return B200IR_E_ALIGN;
+  const ScanPlan pl = make_scan_plan(metric, dtype, nq, N, D, 1, true);
+  if (!workspace || workspace_bytes < pl.total_bytes) return B200IR_E_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return B200IR_E_ALIGN;
+  const MetricParams mp = make_params(metric, flags, D, weights_host);
+  return int(run_scan(pl, dtype, Q, nq, X, N, D, 1, mp, static_cast<unsigned char*>(workspace), out,
+                      static_cast<cudaStream_t>(stream)));
+}
+
+int b200ir_topk_merge(int descending, const float* score, const int64_t* idx, int R, int64_t nq, int k,
+                      float* out_score, int64_t* out_idx, void* stream) {
+  if (R < 1 || nq < 0) return B200IR_E_ARG;
+  if (k < 1 || k > B200IR_MAX_K) return B200IR_E_K;
+  if (nq == 0) return 0;
+  if (!score || !idx || !out_score || !out_idx) return B200IR_E_ARG;
+  return int(launch_merge(descending ? 1 : 0, score, idx, R, nq, k, out_score, out_idx, static_cast<cudaStream_t>(stream)));
+}
+
+int b200ir_histogram(int colorspace, const uint8_t* img, int64_t B, int H, int W, int bins_per_channel,
+                     uint32_t* out_counts, void* stream) {
+  if ((colorspace != B200IR_RGB && colorspace != B200IR_HSV) || B < 0 || H <= 0 || W <= 0) return B200IR_E_ARG;
+  if (bins_per_channel != 8) return B200IR_E_SHAPE;
+  if (B == 0) return 0;
+  if (!img || !out_counts) return B200IR_E_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t pixels = int64_t(H) * W;
+  int slices = int(ceil_div64(pixels, 65536));
+  slices = slices < 1 ? 1 : (slices > 64 ? 64 : slices);
+  if (B * slices > 0x7fffffff) return B200IR_E_SHAPE;
+  const int vector_ok = ((reinterpret_cast<uintptr_t>(img) & 15) == 0 && pixels % 16 == 0) ? 1 : 0;
+  cudaError_t e;
+  if (slices > 1) {
+    e = cudaMemsetAsync(out_counts, 0, size_t(B) * kHistBins * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return int(e);
+  }
+  if (colorspace == B200IR_HSV) {
+    e = init_hsv_tables();
+    if (e != cudaSuccess) return int(e);
+    histogram_kernel<true><<<unsigned(B * slices), kHistThreads, 0, st>>>(img, pixels, slices, vector_ok, out_counts);
+  } else {
+    histogram_kernel<false><<<unsigned(B * slices), kHistThreads, 0, st>>>(img, pixels, slices, vector_ok, out_counts);
+  }
+  return int(cudaGetLastError());
+}
+
+int b200ir_counts_to_embedding(const uint32_t* counts, int64_t B, int nb, float* raw_out, float* unit_out,
+                               float* mag_out, void* stream) {
+  if (B < 0 || nb <= 0) return B200IR_E_ARG;
+  if (B == 0) return 0;
+  if (!counts) return B200IR_E_ARG;
+  counts_to_embedding_kernel<<<unsigned(B), 128, 0, static_cast<cudaStream_t>(stream)>>>(counts, nb, raw_out, unit_out, mag_out);
+  return int(cudaGetLastError());
+}
+
+}  // extern "C"

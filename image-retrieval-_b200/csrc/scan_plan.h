@@ -1,0 +1,99 @@
+// Host-side plan of the CUDA-core scan: tiling, partitioning and workspace layout.
+#pragma once
+#include "common.cuh"
+
+namespace b200ir {
+
+enum ScanKind { K_L1 = 0, K_L2 = 1, K_LINF = 2, K_DOT = 3, K_MULTI = 4 };
+
+constexpr int kScanThreads = 128;   // == rows per tile (one row per thread)
+constexpr int kScanStages = 4;
+constexpr int kRowChunkBytes = 128; // bytes of one row staged per pipeline step
+
+__host__ __device__ inline int scan_kind_of(int metric) {
+  switch (metric) {
+    case B200IR_L1: return K_L1;
+    case B200IR_L2: return K_L2;
+    case B200IR_LINF: return K_LINF;
+    case B200IR_OPTIMIZED: return K_MULTI;
+    default: return K_DOT;   // cosine family + magnitude difference
+  }
+}
+
+struct ScanArgs {
+  const void* X;          // [N, D] database shard, element type T
+  int64_t N;
+  int D;
+  const float* Qf;        // prepared queries fp32 [nq_pad, D_pad], zero padded
+  const float* qnorm;     // [nq_pad] |q|
+  int nq;
+  int D_pad;              // multiple of the row chunk (32 fp32 / 64 bf16 elements)
+  int G;                  // query groups of TQ
+  int P;                  // row partitions
+  int64_t rows_per_part;  // multiple of 128
+  int k;
+  int sortn;              // 256 or 512: capacity of the per-query candidate buffer
+  int aligned;            // rows are 16-byte aligned -> cp.async path
+  uint64_t* partial;      // [nq, P, k] sorted keys            (top-k mode)
+  float* out_all;         // [nq, N] metric values, or nullptr  (pairwise mode)
+  MetricParams mp;
+};
+
+struct ScanPlan {
+  int TQ, G, P, sortn, D_pad, nq_pad;
+  int64_t rows_per_part;
+  size_t smem;
+  size_t off_qf, off_qn, off_partial, total_bytes;
+};
+
+inline int scan_sortn(int k) { return k <= 128 ? 256 : 512; }
+
+inline ScanPlan make_scan_plan(int metric, int dtype, int64_t nq, int64_t N, int D, int k, bool pairwise) {
+  ScanPlan pl{};
+  const int kind = scan_kind_of(metric);
+  const int esz = dtype == B200IR_F32 ? 4 : 2;
+  const int DKE = kRowChunkBytes / esz;
+  const int tq_max = (kind == K_MULTI) ? 4 : 8;
+  pl.TQ = nq <= 1 ? 1 : (nq <= 4 ? 4 : tq_max);
+  pl.G = int(ceil_div64(nq, pl.TQ));
+  pl.nq_pad = pl.G * pl.TQ;
+  pl.D_pad = int(round_up64(D, DKE));
+  pl.sortn = pairwise ? 256 : scan_sortn(k);
+  pl.smem = size_t(kScanStages) * (kScanThreads * kRowChunkBytes + pl.TQ * DKE * 4)
+            + size_t(pl.TQ) * pl.sortn * 8 + pl.TQ * 16;
+  int ctas_per_sm = int((200 * 1024) / pl.smem);
+  ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+  const int64_t target = int64_t(kNumSMs) * ctas_per_sm;
+  int64_t P = target / pl.G;
+  if (P < 1) P = 1;
+  const int64_t ntiles = ceil_div64(N, kScanThreads);
+  if (P > ntiles) P = ntiles;
+  if (P < 1) P = 1;
+  pl.rows_per_part = round_up64(ceil_div64(N, P), kScanThreads);
+  if (pl.rows_per_part < kScanThreads) pl.rows_per_part = kScanThreads;
+  pl.P = int(ceil_div64(N, pl.rows_per_part));
+  if (pl.P < 1) pl.P = 1;
+  size_t off = 0;
+  pl.off_qf = off; off += round_up64(size_t(pl.nq_pad) * pl.D_pad * 4, 256);
+  pl.off_qn = off; off += round_up64(size_t(pl.nq_pad) * 4, 256);
+  pl.off_partial = off;
+  if (!pairwise) off += round_up64(size_t(nq) * pl.P * k * 8, 256);
+  pl.total_bytes = off;
+  return pl;
+}
+
+// one translation unit per (kind, dtype): scan_inst.cu compiled with -DSCAN_KIND / -DSCAN_BF16
+#define B200IR_DECL_SCAN(kind) \
+  cudaError_t launch_scan_##kind##_f32(const ScanArgs& a, int TQ, size_t smem, cudaStream_t st); \
+  cudaError_t launch_scan_##kind##_bf16(const ScanArgs& a, int TQ, size_t smem, cudaStream_t st);
+B200IR_DECL_SCAN(K_L1) B200IR_DECL_SCAN(K_L2) B200IR_DECL_SCAN(K_LINF) B200IR_DECL_SCAN(K_DOT) B200IR_DECL_SCAN(K_MULTI)
+#undef B200IR_DECL_SCAN
+
+cudaError_t launch_prep_queries(int dtype, const void* Q, int nq, int D, int nq_pad, int D_pad, float* Qf, float* qn,
+                                cudaStream_t st);
+
+// Runs prep + scan.  In top-k mode leaves [nq, P, k] sorted keys at ws + plan.off_partial.
+cudaError_t run_scan(const ScanPlan& pl, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D, int k,
+                     const MetricParams& mp, unsigned char* ws, float* out_all, cudaStream_t st);
+
+}  // namespace b200ir

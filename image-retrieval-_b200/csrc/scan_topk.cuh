@@ -1,0 +1,305 @@
+// CUDA-core distance scan with fused top-k (K5/K6 of SURVEY.md section 2.2, plus the exact
+// fp32 forms of L2 / cosine / magnitude / weighted "optimized" similarity).
+//
+// Replaces the per-pair Python loops of app_pipeline.py:156-168 / :296-328 and
+// geometric_metrics.py:12-57: one CTA streams a contiguous range of database rows through
+// shared memory (cp.async, 128-byte swizzled row chunks), every thread owns ONE database row of
+// the current 128-row tile and accumulates its distance to TQ queries at once (queries are
+// broadcast reads from shared memory), and winners go through a per-query threshold filter into
+// a shared-memory candidate buffer that is compacted by a warp-wide bitonic sort.  The distance
+// matrix never reaches HBM; each CTA emits k sorted 64-bit keys per query.
+#pragma once
+#include "common.cuh"
+#include "scan_plan.h"
+
+namespace b200ir {
+
+// |q| and fp32 copy of the queries, padded with zeros to [nq_pad, D_pad].  One warp per row.
+template <typename T>
+__global__ void prep_queries_kernel(const T* __restrict__ Q, int nq, int D, int nq_pad, int D_pad,
+                                    float* __restrict__ Qf, float* __restrict__ qnorm) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= nq_pad) return;
+  float ss = 0.f;
+  for (int d0 = 0; d0 < D_pad; d0 += 32) {
+    const int d = d0 + lane;
+    float v = 0.f;
+    if (warp < nq && d < D) v = to_f32<T>(Q[int64_t(warp) * D + d]);
+    if (d < D_pad) Qf[int64_t(warp) * D_pad + d] = v;
+    float p = v * v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    ss += p;
+  }
+  if (lane == 0) qnorm[warp] = sqrtf(ss);
+}
+
+// Warp-cooperative compaction of one query's candidate buffer: sort, keep the best k.
+template <int E>
+__device__ __noinline__ void compact_candidates(uint64_t* keys, int* cnt, uint64_t* thr, int k, int lane) {
+  const int n = *cnt;
+  uint64_t r[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    r[e] = i < n ? keys[i] : kKeyInf;
+  }
+  warp_sort<E>(r, lane);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    if (i < k) keys[i] = r[e];
+  }
+  const int kept = n < k ? n : k;
+  // threshold = current k-th best key (a candidate must be strictly smaller to enter)
+  const int src_lane = (k - 1) / E, src_e = (k - 1) % E;
+  uint64_t kth = kKeyInf;
+#pragma unroll
+  for (int e = 0; e < E; ++e) if (e == src_e) kth = r[e];
+  kth = shfl_u64(kth, src_lane);
+  if (lane == 0) { *cnt = kept; *thr = (n >= k) ? kth : kKeyInf; }
+  __syncwarp();
+}
+
+template <int KIND>
+__device__ __forceinline__ void accum(float (&a)[KIND == K_MULTI ? 4 : 1], float x, float q) {
+  if constexpr (KIND == K_L1) a[0] += fabsf(x - q);
+  else if constexpr (KIND == K_L2) { const float d = x - q; a[0] = fmaf(d, d, a[0]); }
+  else if constexpr (KIND == K_LINF) a[0] = fmaxf(a[0], fabsf(x - q));
+  else if constexpr (KIND == K_DOT) a[0] = fmaf(x, q, a[0]);
+  else { const float d = x - q; a[0] = fmaf(x, q, a[0]); a[1] += fabsf(d); a[2] = fmaf(d, d, a[2]); a[3] = fmaxf(a[3], fabsf(d)); }
+}
+
+// rank value r (smaller = better) of one (query,row) pair from its accumulators
+template <int KIND>
+__device__ __forceinline__ float finish_rank(const float* acc, float xsq, float qn, const MetricParams& mp) {
+  if constexpr (KIND == K_L1 || KIND == K_L2 || KIND == K_LINF) {
+    return acc[0];
+  } else {
+    const float xn = sqrtf(xsq);
+    float cs = 0.f;
+    if (qn != 0.f && xn != 0.f) cs = acc[0] / (qn * xn);        // geometric_metrics.py:14-18
+    if constexpr (KIND == K_DOT) {
+      if (mp.metric == B200IR_MAG_DIFF) return fabsf(qn - xn);   // geometric_metrics.py:57
+      if (mp.flags & B200IR_FLAG_ABS_SCORE) cs = fabsf(cs);      // app_pipeline.py:167
+      return -cs;
+    } else {
+      const float fD = float(mp.D);
+      float sim = mp.w[0] * cs - mp.w[1] * (acc[1] / fD) - mp.w[2] * (sqrtf(acc[2]) / sqrtf(fD))
+                  - mp.w[3] * acc[3] - mp.w[4] * fabsf(qn - xn);   // geometric_metrics.py:85-92
+      if (mp.flags & B200IR_FLAG_ABS_SCORE) sim = fabsf(sim);
+      return -sim;
+    }
+  }
+}
+
+template <int KIND, typename T, int TQ>
+__global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs a) {
+  constexpr int DKE = kRowChunkBytes / int(sizeof(T));     // elements of a row per pipeline step
+  constexpr int NA = (KIND == K_MULTI) ? 4 : 1;
+  constexpr bool NEED_XSQ = (KIND == K_DOT || KIND == K_MULTI);
+  constexpr int XT_BYTES = kScanThreads * kRowChunkBytes;  // 16 KB database tile per stage
+  constexpr int QC_BYTES = TQ * DKE * 4;                   // fp32 query chunk per stage
+  constexpr int STAGE_BYTES = XT_BYTES + QC_BYTES;
+
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* stage_base = smem;
+  uint64_t* keys_s = reinterpret_cast<uint64_t*>(smem + kScanStages * STAGE_BYTES);
+  uint64_t* thr_s = keys_s + size_t(TQ) * a.sortn;
+  int* cnt_s = reinterpret_cast<int*>(thr_s + TQ);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = blockIdx.x % a.G;
+  const int p = blockIdx.x / a.G;
+  const int64_t row_begin = int64_t(p) * a.rows_per_part;
+  const int64_t row_end = min(a.N, row_begin + a.rows_per_part);
+  const int ntiles = int(ceil_div64(row_end - row_begin, kScanThreads));
+  const int nchunks = a.D_pad / DKE;
+  const int total = ntiles * nchunks;
+  const bool topk_mode = a.out_all == nullptr;
+  const unsigned char* Xb = static_cast<const unsigned char*>(a.X);
+  const int64_t row_bytes = int64_t(a.D) * int64_t(sizeof(T));
+
+  if (tid < TQ) { thr_s[tid] = kKeyInf; cnt_s[tid] = 0; }
+
+  auto issue = [&](int it) {
+    if (it < total) {
+      const int tile = it / nchunks, chunk = it - tile * nchunks;
+      unsigned char* sb = stage_base + (it % kScanStages) * STAGE_BYTES;
+      const int64_t row0 = row_begin + int64_t(tile) * kScanThreads;
+      const int64_t col_byte0 = int64_t(chunk) * kRowChunkBytes;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int id = i * kScanThreads + tid;
+        const int r = id >> 3, c = id & 7;
+        const int64_t grow = row0 + r;
+        const int64_t cb = col_byte0 + c * 16;
+        int nbytes = 0;
+        if (grow < row_end) nbytes = int(max(int64_t(0), min(int64_t(16), row_bytes - cb)));
+        const uint32_t dst = smem_u32(sb + r * kRowChunkBytes + ((c ^ (r & 7)) << 4));
+        const unsigned char* src = nbytes > 0 ? Xb + grow * row_bytes + cb : Xb;
+        if (a.aligned) {
+          cp_async_16(dst, src, nbytes);
+        } else {
+          // rows not 16-byte aligned: element loads, staged through registers
+          T tmp[16 / sizeof(T)];
+#pragma unroll
+          for (int e = 0; e < int(16 / sizeof(T)); ++e)
+            tmp[e] = (int(e * sizeof(T)) < nbytes) ? reinterpret_cast<const T*>(src)[e] : T(0.f);
+          *reinterpret_cast<uint4*>(sb + r * kRowChunkBytes + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<uint4*>(tmp);
+        }
+      }
+      // fp32 query chunk: TQ rows x DKE floats (workspace copy is padded: no guards needed)
+      for (int id = tid; id < TQ * DKE / 4; id += kScanThreads) {
+        const int t = id / (DKE / 4), c = id % (DKE / 4);
+        const float* src = a.Qf + int64_t(g * TQ + t) * a.D_pad + chunk * DKE + c * 4;
+        cp_async_16(smem_u32(sb + XT_BYTES + (t * DKE + c * 4) * 4), src, 16);
+      }
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int s = 0; s < kScanStages - 1; ++s) issue(s);
+
+  float acc[TQ][NA];
+  float xsq = 0.f;
+#pragma unroll
+  for (int t = 0; t < TQ; ++t)
+#pragma unroll
+    for (int j = 0; j < NA; ++j) acc[t][j] = 0.f;
+
+  float qn[TQ];
+#pragma unroll
+  for (int t = 0; t < TQ; ++t) qn[t] = a.qnorm[g * TQ + t];
+
+  for (int it = 0; it < total; ++it) {
+    cp_async_wait<kScanStages - 2>();
+    __syncthreads();
+    issue(it + kScanStages - 1);
+
+    const unsigned char* sb = stage_base + (it % kScanStages) * STAGE_BYTES;
+    const unsigned char* xrow = sb + tid * kRowChunkBytes;
+    const float* qs = reinterpret_cast<const float*>(sb + XT_BYTES);
+
+    float part[TQ][NA];
+    float xpart = 0.f;
+#pragma unroll
+    for (int t = 0; t < TQ; ++t)
+#pragma unroll
+      for (int j = 0; j < NA; ++j) part[t][j] = (KIND == K_LINF || j == 3) ? acc[t][j] : 0.f;
+
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(xrow + ((j ^ (tid & 7)) << 4));
+      if constexpr (sizeof(T) == 4) {
+        const float x[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
+        if constexpr (NEED_XSQ) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) xpart = fmaf(x[e], x[e], xpart);
+        }
+#pragma unroll
+        for (int t = 0; t < TQ; ++t) {
+          const float4 q4 = *reinterpret_cast<const float4*>(qs + t * DKE + j * 4);
+          accum<KIND>(part[t], x[0], q4.x); accum<KIND>(part[t], x[1], q4.y);
+          accum<KIND>(part[t], x[2], q4.z); accum<KIND>(part[t], x[3], q4.w);
+        }
+      } else {
+        const float x[8] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y),
+                            bf16_lo(raw.z), bf16_hi(raw.z), bf16_lo(raw.w), bf16_hi(raw.w)};
+        if constexpr (NEED_XSQ) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xpart = fmaf(x[e], x[e], xpart);
+        }
+#pragma unroll
+        for (int t = 0; t < TQ; ++t) {
+          const float4 qa = *reinterpret_cast<const float4*>(qs + t * DKE + j * 8);
+          const float4 qb = *reinterpret_cast<const float4*>(qs + t * DKE + j * 8 + 4);
+          accum<KIND>(part[t], x[0], qa.x); accum<KIND>(part[t], x[1], qa.y);
+          accum<KIND>(part[t], x[2], qa.z); accum<KIND>(part[t], x[3], qa.w);
+          accum<KIND>(part[t], x[4], qb.x); accum<KIND>(part[t], x[5], qb.y);
+          accum<KIND>(part[t], x[6], qb.z); accum<KIND>(part[t], x[7], qb.w);
+        }
+      }
+    }
+    // two-level summation: chunk partial -> row total (keeps fp32 error ~ sqrt-free (DKE + D/DKE) eps)
+#pragma unroll
+    for (int t = 0; t < TQ; ++t)
+#pragma unroll
+      for (int j = 0; j < NA; ++j) acc[t][j] = (KIND == K_LINF || j == 3) ? part[t][j] : acc[t][j] + part[t][j];
+    xsq += xpart;
+
+    const int tile = it / nchunks, chunk = it - tile * nchunks;
+    if (chunk == nchunks - 1) {
+      const int64_t grow = row_begin + int64_t(tile) * kScanThreads + tid;
+      const bool valid = grow < row_end;
+#pragma unroll
+      for (int t = 0; t < TQ; ++t) {
+        const int q = g * TQ + t;
+        if (valid && q < a.nq) {
+          const float r = finish_rank<KIND>(acc[t], xsq, qn[t], a.mp);
+          if (topk_mode) {
+            const uint64_t key = make_key(r, uint32_t(grow));
+            if (key < thr_s[t]) {
+              const int slot = atomicAdd(&cnt_s[t], 1);
+              keys_s[size_t(t) * a.sortn + slot] = key;
+            }
+          } else {
+            a.out_all[int64_t(q) * a.N + grow] = rank_to_score(r, a.mp.metric, a.mp.flags, a.mp.D);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NA; ++j) acc[t][j] = 0.f;
+      }
+      xsq = 0.f;
+      if (topk_mode) {
+        __syncthreads();
+        for (int t = warp; t < TQ; t += kScanThreads / 32) {
+          if (cnt_s[t] > a.sortn - kScanThreads) {
+            if (a.sortn == 256) compact_candidates<8>(keys_s + size_t(t) * a.sortn, &cnt_s[t], &thr_s[t], a.k, lane);
+            else compact_candidates<16>(keys_s + size_t(t) * a.sortn, &cnt_s[t], &thr_s[t], a.k, lane);
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  if (topk_mode) {
+    __syncthreads();
+    for (int t = warp; t < TQ; t += kScanThreads / 32) {
+      const int q = g * TQ + t;
+      if (q >= a.nq) continue;
+      uint64_t* kb = keys_s + size_t(t) * a.sortn;
+      if (a.sortn == 256) compact_candidates<8>(kb, &cnt_s[t], &thr_s[t], a.k, lane);
+      else compact_candidates<16>(kb, &cnt_s[t], &thr_s[t], a.k, lane);
+      const int kept = cnt_s[t];
+      uint64_t* dst = a.partial + (int64_t(q) * a.P + p) * a.k;
+      for (int i = lane; i < a.k; i += 32) dst[i] = i < kept ? kb[i] : kKeyInf;
+    }
+  }
+}
+
+
+template <int KIND, typename T, int TQ>
+inline cudaError_t launch_scan_inst(const ScanArgs& a, size_t smem, cudaStream_t st) {
+  auto kern = scan_topk_kernel<KIND, T, TQ>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  kern<<<a.G * a.P, kScanThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <int KIND, typename T>
+inline cudaError_t launch_scan_tq(const ScanArgs& a, int TQ, size_t smem, cudaStream_t st) {
+  switch (TQ) {
+    case 1: return launch_scan_inst<KIND, T, 1>(a, smem, st);
+    case 4: return launch_scan_inst<KIND, T, 4>(a, smem, st);
+    case 8:
+      if constexpr (KIND != K_MULTI) return launch_scan_inst<KIND, T, 8>(a, smem, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace b200ir

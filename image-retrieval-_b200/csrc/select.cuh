@@ -1,0 +1,125 @@
+// Selection kernels: merge of per-partition key lists into the final top-k (+ metric transform),
+// and the cross-shard merge that follows the all-gather of a row-sharded search.
+#pragma once
+#include "common.cuh"
+
+namespace b200ir {
+
+// One warp per query: stream P*k sorted-or-not keys through a 32*E-wide bitonic sorter, keeping
+// the best k between rounds.  Writes the reference-normalised score and the global index.
+template <int E>
+__global__ void __launch_bounds__(128) finalize_topk_kernel(const uint64_t* __restrict__ partial, int nq, int64_t per_query,
+                                                           int k, MetricParams mp, int64_t index_offset,
+                                                           float* __restrict__ out_score, int64_t* __restrict__ out_idx) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const uint64_t* src = partial + int64_t(q) * per_query;
+  uint64_t r[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) r[e] = kKeyInf;
+  int kept = 0;
+  int64_t pos = 0;
+  do {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = lane * E + e;
+      if (i >= kept) {
+        const int64_t s = pos + (i - kept);
+        r[e] = s < per_query ? src[s] : kKeyInf;
+      }
+    }
+    pos += 32 * E - kept;
+    warp_sort<E>(r, lane);
+    kept = k;
+  } while (pos < per_query);
+  const bool desc = metric_descending(mp.metric);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    if (i < k) {
+      const uint64_t key = r[e];
+      float sc;
+      int64_t id;
+      if (key == kKeyInf) { sc = desc ? -INFINITY : INFINITY; id = -1; }
+      else { sc = rank_to_score(key_rank(key), mp.metric, mp.flags, mp.D); id = int64_t(key_index(key)) + index_offset; }
+      out_score[int64_t(q) * k + i] = sc;
+      out_idx[int64_t(q) * k + i] = id;
+    }
+  }
+}
+
+// Cross-shard merge: score/idx [R, nq, k] -> [nq, k] ordered by (score, global idx).
+template <int E>
+__global__ void __launch_bounds__(128) merge_topk_kernel(int descending, const float* __restrict__ score,
+                                                        const int64_t* __restrict__ idx, int R, int nq, int k,
+                                                        float* __restrict__ out_score, int64_t* __restrict__ out_idx) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const key128_t kInf = ~key128_t(0);
+  const int64_t per_query = int64_t(R) * k;
+  key128_t r[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) r[e] = kInf;
+  int kept = 0;
+  int64_t pos = 0;
+  do {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = lane * E + e;
+      if (i >= kept) {
+        const int64_t s = pos + (i - kept);
+        key128_t key = kInf;
+        if (s < per_query) {
+          const int shard = int(s / k), j = int(s % k);
+          const int64_t off = (int64_t(shard) * nq + q) * k + j;
+          const int64_t id = idx[off];
+          if (id >= 0) {
+            const float v = score[off];
+            key = (key128_t(f32_to_ordered(descending ? -v : v)) << 64) | key128_t(uint64_t(id));
+          }
+        }
+        r[e] = key;
+      }
+    }
+    pos += 32 * E - kept;
+    warp_sort<E>(r, lane);
+    kept = k;
+  } while (pos < per_query);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    if (i < k) {
+      const key128_t key = r[e];
+      float sc;
+      int64_t id;
+      if (key == kInf) { sc = descending ? -INFINITY : INFINITY; id = -1; }
+      else {
+        const float v = ordered_to_f32(uint32_t(uint64_t(key >> 64)));
+        sc = descending ? 0.0f - v : v;
+        id = int64_t(uint64_t(key));
+      }
+      out_score[int64_t(q) * k + i] = sc;
+      out_idx[int64_t(q) * k + i] = id;
+    }
+  }
+}
+
+inline cudaError_t launch_finalize(const uint64_t* partial, int64_t nq, int64_t per_query, int k, const MetricParams& mp,
+                                   int64_t index_offset, float* out_score, int64_t* out_idx, cudaStream_t st) {
+  const int blocks = int(ceil_div64(nq, 4));
+  if (k <= 128) finalize_topk_kernel<8><<<blocks, 128, 0, st>>>(partial, int(nq), per_query, k, mp, index_offset, out_score, out_idx);
+  else finalize_topk_kernel<16><<<blocks, 128, 0, st>>>(partial, int(nq), per_query, k, mp, index_offset, out_score, out_idx);
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch_merge(int descending, const float* score, const int64_t* idx, int R, int64_t nq, int k,
+                                float* out_score, int64_t* out_idx, cudaStream_t st) {
+  const int blocks = int(ceil_div64(nq, 4));
+  if (k <= 128) merge_topk_kernel<8><<<blocks, 128, 0, st>>>(descending, score, idx, R, int(nq), k, out_score, out_idx);
+  else merge_topk_kernel<16><<<blocks, 128, 0, st>>>(descending, score, idx, R, int(nq), k, out_score, out_idx);
+  return cudaGetLastError();
+}
+
+}  // namespace b200ir

@@ -1,0 +1,216 @@
+"""Batched operators over the C ABI (include/b200ir.h): the new, vectorised face of the hot path.
+
+PyTorch is plumbing here (device memory, streams); every number is produced by libb200ir.so.
+Tensors are passed as raw device pointers on torch's current CUDA stream.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ANGLE, BF16, COS_DIST, COS_SIM, F32, FLAG_ABS_SCORE, FLAG_NO_RERANK, FLAG_NO_TENSOR, FLAG_RAW,
+                   HSV, L1, L2, LINF, MAG_DIFF, MAX_K, OPTIMIZED, RGB, B200IRError)
+
+METRIC_IDS = {
+    "l1": L1, "l1_distance": L1,
+    "l2": L2, "l2_distance": L2,
+    "linf": LINF, "linf_distance": LINF,
+    "cosine_similarity": COS_SIM, "cosine": COS_SIM,
+    "cosine_distance": COS_DIST,
+    "angular_distance": ANGLE, "angle": ANGLE,
+    "magnitude_difference": MAG_DIFF,
+    "optimized_similarity": OPTIMIZED,
+}
+DESCENDING = {COS_SIM, OPTIMIZED}
+WEIGHT_KEYS = ("w_angle", "w_l1", "w_l2", "w_inf", "w_mag")
+
+_workspaces = {}
+
+
+def metric_id(metric):
+    if isinstance(metric, int):
+        return metric
+    try:
+        return METRIC_IDS[metric]
+    except KeyError:
+        raise ValueError(f"unknown metric {metric!r}; one of {sorted(METRIC_IDS)}") from None
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise B200IRError("no CUDA device: this package has no CPU fallback (B200 / sm_100a required)")
+    lib = _lib.load()
+    if not lib.b200ir_device_ok():
+        raise B200IRError("current CUDA device is not compute capability 10.x (B200): libb200ir.so only carries sm_100a code")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
+
+
+def as_device_matrix(a, dtype=None):
+    """numpy / torch (host or device) -> contiguous 2-D CUDA tensor of fp32 or bf16."""
+    dev = device()
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.float32:
+            a = a.astype(np.float32)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    elif isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = torch.as_tensor(np.asarray(a, dtype=np.float32))
+    if t.dim() == 1:
+        t = t.unsqueeze(0)
+    if t.dim() != 2:
+        raise ValueError(f"expected a vector or a matrix, got shape {tuple(t.shape)}")
+    want = dtype if dtype is not None else (t.dtype if t.dtype in (torch.float32, torch.bfloat16) else torch.float32)
+    if t.device != dev:
+        t = t.to(dev, non_blocking=True)
+    if t.dtype != want:
+        t = t.to(want)
+    return t.contiguous()
+
+
+def _dtype_id(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise ValueError(f"unsupported element type {t.dtype}")
+
+
+def _workspace(nbytes, dev):
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
+        _workspaces[key] = ws
+    return ws
+
+
+def _weights(params):
+    if params is None:
+        return None
+    w = (ctypes.c_float * 5)()
+    defaults = (1.0, 0.0, 0.0, 0.0, 0.0)       # geometric_metrics.py:78-82
+    for i, key in enumerate(WEIGHT_KEYS):
+        w[i] = float(params.get(key, defaults[i]))
+    return w
+
+
+def _flags(normalized, abs_score, flags):
+    f = int(flags)
+    if not normalized:
+        f |= FLAG_RAW
+    if abs_score:
+        f |= FLAG_ABS_SCORE
+    return f
+
+
+def row_sqnorms(X):
+    X = as_device_matrix(X)
+    out = torch.empty(X.shape[0], dtype=torch.float32, device=X.device)
+    lib = _lib.load()
+    _lib.check(lib.b200ir_row_sqnorms(_ptr(X), _dtype_id(X), X.shape[0], X.shape[1], _ptr(out), _stream()), "row_sqnorms")
+    return out
+
+
+def topk(Q, X, metric, k, *, index_offset=0, normalized=True, abs_score=False, params=None, flags=0):
+    """Fused distance + top-k.  Returns (scores (nq,k) fp32, indices (nq,k) int64) on the device,
+    best first, ties by ascending index; slots past N hold (+-inf, -1)."""
+    m = metric_id(metric)
+    X = as_device_matrix(X)
+    Q = as_device_matrix(Q, dtype=X.dtype)
+    if Q.shape[1] != X.shape[1]:
+        raise ValueError(f"dimension mismatch: queries {Q.shape[1]} vs database {X.shape[1]}")
+    if not 1 <= k <= MAX_K:
+        raise ValueError(f"k must be in 1..{MAX_K}")
+    lib = _lib.load()
+    nq, D = Q.shape
+    N = X.shape[0]
+    f = _flags(normalized, abs_score, flags)
+    scores = torch.empty((nq, k), dtype=torch.float32, device=X.device)
+    idx = torch.empty((nq, k), dtype=torch.int64, device=X.device)
+    need = lib.b200ir_topk_workspace_bytes(m, _dtype_id(X), nq, N, D, k, f)
+    ws = _workspace(need, X.device)
+    st = lib.b200ir_topk(m, _dtype_id(X), _ptr(Q), nq, _ptr(X), N, D, k, int(index_offset), f, _weights(params),
+                         _ptr(scores), _ptr(idx), _ptr(ws), ws.numel(), _stream())
+    _lib.check(st, "topk")
+    return scores, idx
+
+
+def pairwise(Q, X, metric, *, normalized=True, abs_score=False, params=None, flags=0):
+    """(nq, N) fp32 matrix of `metric` (evaluation-sized inputs)."""
+    m = metric_id(metric)
+    X = as_device_matrix(X)
+    Q = as_device_matrix(Q, dtype=X.dtype)
+    if Q.shape[1] != X.shape[1]:
+        raise ValueError(f"dimension mismatch: queries {Q.shape[1]} vs database {X.shape[1]}")
+    lib = _lib.load()
+    nq, D = Q.shape
+    N = X.shape[0]
+    out = torch.empty((nq, N), dtype=torch.float32, device=X.device)
+    if nq == 0 or N == 0:
+        return out
+    need = lib.b200ir_pairwise_workspace_bytes(m, _dtype_id(X), nq, N, D)
+    ws = _workspace(need, X.device)
+    st = lib.b200ir_pairwise(m, _dtype_id(X), _ptr(Q), nq, _ptr(X), N, D, _flags(normalized, abs_score, flags),
+                             _weights(params), _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _lib.check(st, "pairwise")
+    return out
+
+
+def topk_merge(scores, idx, descending):
+    """Merge per-shard lists: scores/idx (R, nq, k) -> (nq, k) ordered by (score, global index)."""
+    device()
+    scores = scores.contiguous()
+    idx = idx.contiguous()
+    R, nq, k = scores.shape
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=scores.device)
+    lib = _lib.load()
+    _lib.check(lib.b200ir_topk_merge(1 if descending else 0, _ptr(scores), _ptr(idx), R, nq, k, _ptr(out_s), _ptr(out_i),
+                                     _stream()), "topk_merge")
+    return out_s, out_i
+
+
+def histogram(images, colorspace="rgb"):
+    """(B,H,W,3) uint8 RGB -> (B,512) int32 counts on the device (8x8x8 joint bins)."""
+    dev = device()
+    if isinstance(images, np.ndarray):
+        images = torch.from_numpy(np.ascontiguousarray(images))
+    if images.dtype != torch.uint8:
+        raise ValueError("images must be uint8")
+    if images.dim() == 3:
+        images = images.unsqueeze(0)
+    if images.dim() != 4 or images.shape[-1] != 3:
+        raise ValueError(f"expected (B,H,W,3) uint8, got {tuple(images.shape)}")
+    if images.device != dev:
+        images = images.to(dev, non_blocking=True)
+    images = images.contiguous()
+    B, H, W, _ = images.shape
+    counts = torch.empty((B, 512), dtype=torch.int32, device=dev)
+    cs = {"rgb": RGB, "hsv": HSV}[colorspace]
+    lib = _lib.load()
+    _lib.check(lib.b200ir_histogram(cs, _ptr(images), B, H, W, 8, _ptr(counts), _stream()), "histogram")
+    return counts
+
+
+def counts_to_embedding(counts):
+    """(B,nb) int32 counts -> (raw fp32 (B,nb), unit-norm fp32 (B,nb), magnitude fp32 (B,))."""
+    device()
+    counts = counts.contiguous()
+    B, nb = counts.shape
+    raw = torch.empty((B, nb), dtype=torch.float32, device=counts.device)
+    unit = torch.empty_like(raw)
+    mag = torch.empty(B, dtype=torch.float32, device=counts.device)
+    lib = _lib.load()
+    _lib.check(lib.b200ir_counts_to_embedding(_ptr(counts), B, nb, _ptr(raw), _ptr(unit), _ptr(mag), _stream()),
+               "counts_to_embedding")
+    return raw, unit, mag

@@ -1,0 +1,56 @@
+"""Row-sharded multi-GPU search: one process per GPU, each rank owns a
+contiguous range of database rows, runs the fused distance + top-k locally with its row base as
+`index_offset`, and ONE all-gather of the packed (score, index) lists feeds the final merge on
+every rank.  No other data-path collective exists: the scan itself is embarrassingly parallel.
+
+The local search and the merge are injectable so that the sharding / collective logic can be
+exercised with the gloo backend on CPU (tests/test_sharded_cpu.py injects the oracle); the
+defaults are the CUDA operators and there is no CPU fallback in the product path.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def shard_range(n_rows, world_size, rank):
+    """Contiguous balanced split: the first n_rows % world_size ranks own one extra row."""
+    base, rem = divmod(int(n_rows), int(world_size))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def _default_local(Q, X, metric, k, index_offset, **kw):
+    return ops.topk(Q, X, metric, k, index_offset=index_offset, **kw)
+
+
+def _default_merge(scores, idx, descending):
+    return ops.topk_merge(scores, idx, descending)
+
+
+class ShardedIndex:
+    def __init__(self, local_rows, row_begin, group=None, local_topk=None, merge=None):
+        self.X = local_rows
+        self.row_begin = int(row_begin)
+        self.group = group
+        self.local_topk = local_topk or _default_local
+        self.merge = merge or _default_merge
+
+    def topk(self, Q, metric, k, **kw):
+        """Global top-k over all shards; every rank returns the same (scores, indices)."""
+        m = ops.metric_id(metric)
+        s, i = self.local_topk(Q, self.X, metric, k, self.row_begin, **kw)
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return s, i
+        R = dist.get_world_size(self.group)
+        nq = s.shape[0]
+        # one collective: pack fp32 scores (as int32 bits) and int64 ids into one int64 payload
+        payload = torch.empty((2, nq, k), dtype=torch.int64, device=s.device)
+        payload[0] = s.contiguous().view(torch.int32).to(torch.int64)
+        payload[1] = i
+        gathered = torch.empty(R * payload.numel(), dtype=torch.int64, device=s.device)
+        dist.all_gather_into_tensor(gathered, payload.view(-1), group=self.group)
+        gathered = gathered.view(R, 2, nq, k)
+        all_s = gathered[:, 0].to(torch.int32).view(torch.float32).contiguous()
+        all_i = gathered[:, 1].contiguous()
+        return self.merge(all_s, all_i, m in ops.DESCENDING)

@@ -1,0 +1,141 @@
+/*
+ * b200ir.h - C ABI of the B200-native brute-force retrieval hot path.
+ *
+ * This is the drop-in boundary for the path BASELINE.json's north_star names.  The
+ * reference (MeltingCrystals/Image-Retrieval-) is pure Python and has no FFI of its own
+ * (SURVEY.md section 8b): the entry points below are what a ctypes binding for that
+ * path binds, one per reference loop they replace (cited per function).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - Every pointer is a DEVICE pointer owned by the caller unless the name ends in
+ *     `_host`.  Work is enqueued on the caller's `stream` (a cudaStream_t passed as
+ *     void*) and is asynchronous; no hidden allocation: scratch is an explicit
+ *     caller-provided workspace sized by the matching *_workspace_bytes() query.
+ *   - Return value: 0 = ok, < 0 = argument error (B200IR_E_*), > 0 = cudaError_t.
+ *     Nothing throws.  b200ir_error_string() names either kind.
+ *   - Output contract of every top-k: row i is sorted best-first, ties broken by
+ *     ascending global index (Python stable sort + slice: app_pipeline.py:171-172,
+ *     image_search.py:199-219); slots past the number of database rows hold
+ *     (+inf | -inf, -1).
+ *   - There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef B200IR_H
+#define B200IR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200IR_VERSION 100
+
+/* metric ids (geometric_metrics.py:11-94) */
+#define B200IR_L1         0   /* sum|a-b| (/D unless RAW)                  :34-39 */
+#define B200IR_L2         1   /* sqrt(sum (a-b)^2) (/sqrt(D) unless RAW)    :42-47 */
+#define B200IR_LINF       2   /* max|a-b|                                   :50-52 */
+#define B200IR_COS_SIM    3   /* dot/(|a||b|), 0 when a norm is 0           :12-18 */
+#define B200IR_COS_DIST   4   /* 1 - cos                                    :29-31 */
+#define B200IR_ANGLE      5   /* arccos(clip(cos,-1,1))                     :21-26 */
+#define B200IR_MAG_DIFF   6   /* | |a| - |b| |                              :55-57 */
+#define B200IR_OPTIMIZED  7   /* w_angle*cos - w_l1*L1n - w_l2*L2n - w_inf*Linf - w_mag*mag  :60-94 */
+#define B200IR_NUM_METRICS 8
+
+/* element types of Q and X (same type for both) */
+#define B200IR_F32  0
+#define B200IR_BF16 1
+
+/* flags */
+#define B200IR_FLAG_RAW        1   /* normalized=False for L1 / L2 (geometric_metrics.py:37,45) */
+#define B200IR_FLAG_ABS_SCORE  2   /* rank COS_SIM / OPTIMIZED by |score| (app_pipeline.py:167)  */
+#define B200IR_FLAG_NO_TENSOR  4   /* force the CUDA-core scan even where the tcgen05 path applies */
+#define B200IR_FLAG_NO_RERANK  8   /* tcgen05 path: skip the exact fp32 re-rank of the candidates */
+
+/* colour spaces of b200ir_histogram */
+#define B200IR_RGB 0
+#define B200IR_HSV 1   /* OpenCV 8-bit RGB2HSV (H in [0,180)), bit-exact */
+
+/* argument errors */
+#define B200IR_E_ARG        (-1)   /* null pointer / negative size / unknown enum */
+#define B200IR_E_K          (-2)   /* k out of range (1..B200IR_MAX_K) */
+#define B200IR_E_WORKSPACE  (-3)   /* workspace missing or too small */
+#define B200IR_E_ALIGN      (-4)   /* pointer not aligned for its element type */
+#define B200IR_E_DEVICE     (-5)   /* not an sm_100 device / kernel image missing */
+#define B200IR_E_SHAPE      (-6)   /* shape not supported by the requested path */
+#define B200IR_MAX_K 256
+
+int b200ir_version(void);
+const char* b200ir_error_string(int status);
+
+/* 1 if the current device can run the library (compute capability 10.x), else 0. */
+int b200ir_device_ok(void);
+
+/*
+ * Row squared norms, out[i] = sum_j X[i][j]^2 in fp32.
+ * Replaces the np.linalg.norm calls repeated per pair at geometric_metrics.py:14-15,57
+ * and app_pipeline.py:161-163.
+ */
+int b200ir_row_sqnorms(const void* X, int dtype, int64_t N, int D, float* out, void* stream);
+
+/*
+ * Fused distance + top-k scan of nq queries against N database rows.
+ * Replaces the per-pair scan loops + list.sort + slice of
+ *   app_pipeline.py:156-172 (search_images), :296-328 (search_with_multiple_metrics),
+ *   image_search.py:98-115 and :173-219 (candidate scoring + per-metric sorts).
+ *
+ *   Q [nq, D], X [N, D] row-major, contiguous, element type `dtype`.
+ *   index_offset: added to every returned index (base of this shard of a row-sharded DB).
+ *   weights_host: 5 floats {w_angle, w_l1, w_l2, w_inf, w_mag} (HOST memory) for
+ *                 B200IR_OPTIMIZED, ignored (may be NULL) otherwise.
+ *   out_score [nq, k] fp32: the metric's reference-normalised value of each winner.
+ *   out_idx   [nq, k] int64: global row ids.
+ * Ranking: distances ascending, COS_SIM / OPTIMIZED descending; COS_DIST and ANGLE are
+ * ranked by descending cosine (monotone), L2 by the squared sum.
+ */
+size_t b200ir_topk_workspace_bytes(int metric, int dtype, int64_t nq, int64_t N, int D, int k, int flags);
+int b200ir_topk(int metric, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D,
+                int k, int64_t index_offset, int flags, const float* weights_host,
+                float* out_score, int64_t* out_idx,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Full (nq, N) metric matrix, same arithmetic as b200ir_topk's CUDA-core scan.
+ * Replaces the pair loops of mi_analysis.py:277-292 / get_all_metrics
+ * (geometric_metrics.py:114-129) for evaluation-sized inputs.
+ */
+size_t b200ir_pairwise_workspace_bytes(int metric, int dtype, int64_t nq, int64_t N, int D);
+int b200ir_pairwise(int metric, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D,
+                    int flags, const float* weights_host, float* out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Merge R per-shard top-k lists (after the all-gather of a row-sharded search):
+ * score [R, nq, k], idx [R, nq, k] -> out_score [nq, k], out_idx [nq, k], ordered by
+ * (score, global index); entries with idx < 0 are padding.  SURVEY.md section 8e.
+ */
+int b200ir_topk_merge(int descending, const float* score, const int64_t* idx, int R, int64_t nq, int k,
+                      float* out_score, int64_t* out_idx, void* stream);
+
+/*
+ * 512-bin joint colour histogram of uint8 images, img [B, H, W, 3] interleaved RGB,
+ * out_counts [B, bins^3] uint32, bin = (c0bin*bins + c1bin)*bins + c2bin with
+ * c*bin = c>>5 (H: h*8/180).  bins_per_channel must be 8.  The embedding producer
+ * named by north_star (no reference code exists: SURVEY.md section 0, 8c).
+ */
+int b200ir_histogram(int colorspace, const uint8_t* img, int64_t B, int H, int W, int bins_per_channel,
+                     uint32_t* out_counts, void* stream);
+
+/*
+ * counts [B, nb] uint32 -> unit-norm fp32 vectors [B, nb] and magnitudes [B]
+ * (ImageEmbeddingSystem.py:88-94: embedding / |embedding|, magnitude).  unit_out or
+ * mag_out may be NULL; raw_out (may be NULL) receives the un-normalised fp32 counts.
+ */
+int b200ir_counts_to_embedding(const uint32_t* counts, int64_t B, int nb,
+                               float* raw_out, float* unit_out, float* mag_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200IR_H */

@@ -1,0 +1,104 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, host-side logic
+(shard ranges, plans via the public size queries, import shim), and that the product refuses to
+compute without a GPU (no silent fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from image_retrieval_b200 import _lib
+    return _lib.load()
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "b200ir.h")).read()
+    declared = set(re.findall(r"\b(b200ir_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 11
+    raw = ctypes.CDLL(os.path.join(ROOT, "image-retrieval-_b200", "libb200ir.so"))
+    for name in declared:
+        assert hasattr(raw, name), f"libb200ir.so does not export {name}"
+    from image_retrieval_b200 import _lib
+    assert set(_lib.EXPORTS) == declared
+
+
+def test_abi_argument_errors_without_gpu(lib):
+    assert lib.b200ir_version() == 100
+    assert b"ok" in lib.b200ir_error_string(0)
+    assert lib.b200ir_topk_workspace_bytes(0, 0, 8, 1000, 512, 10, 0) > 0
+    assert lib.b200ir_topk_workspace_bytes(0, 0, 8, 1000, 512, 0, 0) == 0          # bad k
+    assert lib.b200ir_topk_workspace_bytes(99, 0, 8, 1000, 512, 10, 0) == 0        # bad metric
+    st = lib.b200ir_topk(0, 0, None, 4, None, 10, 16, 300, 0, 0, None, None, None, None, 0, None)
+    assert st == -2 and b"k out of range" in lib.b200ir_error_string(st)
+    st = lib.b200ir_topk(42, 0, None, 4, None, 10, 16, 3, 0, 0, None, None, None, None, 0, None)
+    assert st == -1
+    st = lib.b200ir_histogram(0, None, 1, 8, 8, 16, None, None)
+    assert st == -6
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from image_retrieval_b200 import ops
+    from image_retrieval_b200._lib import B200IRError
+    with pytest.raises(B200IRError):
+        ops.topk(np.zeros((1, 8), np.float32), np.zeros((4, 8), np.float32), "l1", 2)
+    with pytest.raises(B200IRError):
+        ops.histogram(np.zeros((1, 4, 4, 3), np.uint8))
+    from image_retrieval_b200.geometric_metrics import GeometricSimilarityMetrics as G
+    with pytest.raises(B200IRError):
+        G.l1_distance(np.zeros(4), np.ones(4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "image-retrieval-_b200")
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            src = open(os.path.join(pkg, name)).read()
+            assert "oracle" not in src.replace("the oracle", ""), f"{name} references the oracle"
+
+
+def test_shard_range_partitions():
+    from image_retrieval_b200.sharded import shard_range
+    for N in (0, 1, 7, 1000, 10_000_000):
+        for R in (1, 2, 3, 4, 8):
+            spans = [shard_range(N, R, r) for r in range(R)]
+            assert spans[0][0] == 0 and spans[-1][1] == N
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(R - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_surface_names_match_reference():
+    from image_retrieval_b200 import config
+    from image_retrieval_b200.app_pipeline import EnhancedImageSearchApp, SimpleSearcher
+    from image_retrieval_b200.geometric_metrics import GeometricSimilarityMetrics
+    from image_retrieval_b200.image_search import EnhancedTextImageSearcher
+    from image_retrieval_b200.ImageEmbeddingSystem import ImageEmbeddingSystem
+    assert config.EMBEDDING_DIM == 512 and config.SCORE_THRESHOLD == 0.25 and config.BATCH_SIZE == 100
+    for n in ("cosine_similarity", "angular_distance", "cosine_distance", "l1_distance", "l2_distance", "linf_distance",
+              "magnitude_difference", "optimized_similarity", "optimized_distance", "get_all_metrics", "create_parameter_grid"):
+        assert callable(getattr(GeometricSimilarityMetrics, n))
+    for n in ("search_images", "search_with_multiple_metrics", "process_images", "_generate_dummy_embeddings"):
+        assert callable(getattr(EnhancedImageSearchApp, n))
+    for n in ("search", "search_with_multiple_metrics", "compare_search_methods", "set_similarity_params", "generate_text_embedding"):
+        assert callable(getattr(EnhancedTextImageSearcher, n))
+    for n in ("generate_embedding", "process_and_store_images", "get_embeddings", "get_embeddings_with_magnitude",
+              "reconstruct_original_embeddings", "setup_milvus"):
+        assert callable(getattr(ImageEmbeddingSystem, n))
+    s = SimpleSearcher()
+    s.set_similarity_params({"w_l1": 0.5})
+    assert s.similarity_params == {"w_angle": 1.0, "w_l1": 0.5, "w_l2": 0.0, "w_inf": 0.0, "w_mag": 0.0}
+    assert GeometricSimilarityMetrics.create_parameter_grid(3)["w_mag"] == [0.0, 0.5, 1.0]
+    app = EnhancedImageSearchApp()
+    assert app.search_images(np.ones(512)) == []
+    assert app.search_with_multiple_metrics(np.ones(512)) == {'analysis': {'intersections': {}, 'unique_contributions': {}}}

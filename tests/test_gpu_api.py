@@ -1,0 +1,114 @@
+"""GPU tests of the reference-facing Python surface (same names / shapes as the reference)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import metrics as OM
+from oracle import search as OS
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "search_golden.npz"))
+
+
+def test_scalar_metrics_surface(golden_dir):
+    from image_retrieval_b200.geometric_metrics import GeometricSimilarityMetrics as G
+    g = np.load(os.path.join(golden_dir, "metrics_golden.npz"))
+    Q, X = g["Q_512"], g["X_512"]
+    q, x = Q[1], X[6]
+    ref = OM.get_all_metrics(q, x)
+    got = G.get_all_metrics(q, x)
+    assert list(got) == list(ref)
+    for k in ref:
+        np.testing.assert_allclose(got[k], ref[k], rtol=2e-5, atol=4e-6, err_msg=k)
+    assert type(G.l2_distance(q, x)) is np.float64 and type(G.l1_distance(q, x)) is np.float32
+    assert G.cosine_similarity(q, X[0]) == 0.0 and isinstance(G.cosine_similarity(q, X[0]), float)
+    assert G.angular_distance(q, X[0]) == np.pi / 2
+    np.testing.assert_allclose(G.l1_distance(q, x, normalized=False), g["l1_raw_512"][1, 6], rtol=2e-5)
+    p = {"w_angle": 1.0, "w_l1": 1.0, "w_l2": 1.0, "w_inf": 0.0, "w_mag": 0.5}
+    np.testing.assert_allclose(G.optimized_similarity(q, x, p), g["optimized_similarity_512"][1, 6], rtol=1e-4)
+    np.testing.assert_allclose(G.optimized_distance(q, x, p), -g["optimized_similarity_512"][1, 6], rtol=1e-4)
+    np.testing.assert_allclose(G.optimized_similarity(q, x, {}), g["optimized_default_512"][1, 6], rtol=1e-4, atol=4e-6)
+    assert np.array_equal(np.array(G.create_parameter_grid(5)["w_l1"]), g["grid5"])
+
+
+def test_search_images_matches_reference_run(gold):
+    from image_retrieval_b200.app_pipeline import EnhancedImageSearchApp
+    X, Q = gold["X"], gold["Q"]
+    app = EnhancedImageSearchApp()
+    assert app.search_images(Q[0]) == []                                   # empty store (app_pipeline.py:147-149)
+    for i in range(len(X)):
+        app.embeddings[f"img_{i:04d}.jpg"] = X[i]
+    for qi, q in enumerate(Q):
+        res = app.search_images(q, top_k=10)
+        assert [int(r["path"][4:8]) for r in res] == list(gold[f"search_images_idx_{qi}"])
+        np.testing.assert_allclose([r["score"] for r in res], gold[f"search_images_score_{qi}"], rtol=1e-5, atol=2e-6)
+        multi = app.search_with_multiple_metrics(q, top_k=5)
+        for name in ("cosine_similarity", "l1_distance", "l2_distance"):
+            assert [int(r["path"][4:8]) for r in multi[name]] == list(gold[f"multi_{name}_idx_{qi}"]), name
+            np.testing.assert_allclose([r[name] for r in multi[name]], gold[f"multi_{name}_val_{qi}"], rtol=2e-5, atol=2e-6)
+        ref = OS.search_with_multiple_metrics({f"img_{i:04d}.jpg": X[i] for i in range(len(X))}, q, 5)
+        assert multi["analysis"] == ref["analysis"]
+    # optimized similarity branch
+    app.searcher.set_similarity_params({"w_l1": 0.5, "w_mag": 0.25})
+    res = app.search_images(Q[1], top_k=7, use_optimized_similarity=True)
+    emb = {f"img_{i:04d}.jpg": X[i] for i in range(len(X))}
+    ref = OS.search_images(emb, Q[1], 7, True, app.searcher.similarity_params)
+    assert [r["path"] for r in res] == [r["path"] for r in ref]
+    # fast path store
+    app2 = EnhancedImageSearchApp()
+    app2.set_embeddings([f"img_{i:04d}.jpg" for i in range(len(X))], X)
+    assert [r["path"] for r in app2.search_images(Q[2], 10)] == [r["path"] for r in app.search_images(Q[2], 10)]
+    assert app.search_with_multiple_metrics(Q[0], 5).keys() >= {"cosine_similarity", "l1_distance", "l2_distance", "analysis"}
+    assert EnhancedImageSearchApp().search_with_multiple_metrics(Q[0]) == {'analysis': {'intersections': {}, 'unique_contributions': {}}}
+
+
+def test_embedding_system_and_text_searcher(gold):
+    from image_retrieval_b200.ImageEmbeddingSystem import ImageEmbeddingSystem
+    from image_retrieval_b200.image_search import EnhancedTextImageSearcher
+    from oracle import histogram as OH
+    imgs = synth.images_palette(60, 40, 40, 77)
+    sys_ = ImageEmbeddingSystem()
+    assert sys_.process_and_store_images([]) == (0, 0)
+    ok, failed = sys_.process_and_store_images([im for im in imgs[:50]] + ["/nonexistent/file.jpg"])
+    assert (ok, failed) == (50, 1)
+    sys_.store_arrays([f"p{i}" for i in range(50, 60)], imgs[50:])
+    unit, mag = sys_.generate_embedding(imgs[3])
+    ou, om = OH.embedding(imgs[3:4])
+    np.testing.assert_allclose(unit, ou[0], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(mag, om[0], rtol=1e-6)
+    with pytest.raises(Exception):
+        sys_.generate_embedding("/nonexistent/file.jpg")
+    embs = sys_.get_embeddings_with_magnitude(limit=1000)
+    assert len(embs) == 60 and len(sys_.get_embeddings(limit=7)) == 7
+    rec = sys_.reconstruct_original_embeddings(embs)
+    np.testing.assert_allclose(rec[3][1], OH.histogram(imgs[3:4])[0].astype(np.float32), rtol=1e-5, atol=1e-3)
+
+    searcher = EnhancedTextImageSearcher(collection=sys_.collection, text_encoder=lambda t: OH.embedding(imgs[5:6])[0][0])
+    with pytest.raises(ValueError):
+        searcher.search("   ")
+    res = searcher.search("a query", top_k=5)
+    assert len(res) <= 5 and all(r["score"] >= 0.25 for r in res)
+    U = np.stack([e[1] for e in embs])
+    paths = [e[0] for e in embs]
+    q = OH.embedding(imgs[5:6])[0][0]
+    # reference flow with an exact candidate stage (image_search.py:88-140)
+    cos = OM.pairwise(q[None], U, "cosine_similarity", np.float64)[0]
+    order = np.argsort(-cos, kind="stable")[:15]
+    ref = OS.threshold_and_dedupe([{"path": paths[j], "score": cos[j]} for j in order], 5, 0.25, False)
+    assert [r["path"] for r in res] == [r["path"] for r in ref]
+    multi = searcher.search_with_multiple_metrics("a query", top_k=4)
+    assert set(multi) == {"cosine_similarity", "l1_distance", "l2_distance", "linf_distance", "magnitude_difference",
+                          "optimized_similarity", "analysis"}
+    cand = np.argsort(-cos, kind="stable")[:20]
+    for name, m, desc in (("l1_distance", "l1", False), ("linf_distance", "linf", False), ("cosine_similarity", "cosine_similarity", True)):
+        vals = OM.pairwise(q[None], U[cand], m, np.float64)[0]
+        o = np.argsort(-vals if desc else vals, kind="stable")[:4]
+        assert [r["path"] for r in multi[name]] == [paths[cand[j]] for j in o], name
+    cmp = searcher.compare_search_methods("a query", top_k=3)
+    assert set(cmp) == {"standard_results", "optimized_results", "metrics"}

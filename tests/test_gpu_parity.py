@@ -1,0 +1,247 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle.  Run with -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import histogram as OH
+from oracle import metrics as OM
+from oracle import search as OS
+from oracle import synth
+from parity import check_topk
+
+pytestmark = pytest.mark.gpu
+
+METRICS = ["l1", "l2", "linf", "cosine_similarity", "cosine_distance", "angular_distance", "magnitude_difference"]
+PARAMS = {"w_angle": 1.0, "w_l1": 1.0, "w_l2": 1.0, "w_inf": 0.0, "w_mag": 0.5}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from image_retrieval_b200 import ops as o
+    o.device()
+    return o
+
+
+def _tol(metric):
+    # fp32: 1e-5 relative (north_star); cosine-family values come from a difference-prone dot
+    # product, so they also get an absolute floor of 2e-6 (in cosine units).
+    if metric in ("cosine_similarity", "cosine_distance", "optimized_similarity"):
+        return dict(rtol=1e-5, atol=2e-6)
+    if metric == "angular_distance":
+        return dict(rtol=1e-5, atol=1e-5 * np.pi)          # arccos is ill-conditioned near 0 / pi
+    if metric == "magnitude_difference":
+        return dict(rtol=1e-5, atol=1e-5)                  # difference of two norms ~ sqrt(D)
+    return dict(rtol=1e-5, atol=1e-30)
+
+
+# ------------------------------------------------------------------------------- pairwise values
+@pytest.mark.parametrize("D", [1, 3, 7, 33, 64, 512, 2048])
+@pytest.mark.parametrize("metric", METRICS + ["optimized_similarity"])
+def test_pairwise_fp32_vs_oracle(ops, D, metric):
+    Q = synth.gaussian(5, D, 100 + D)
+    X = synth.gaussian(300, D, 200 + D)
+    X[0] = 0
+    X[1] = Q[0]
+    kw = {"params": PARAMS} if metric == "optimized_similarity" else {}
+    got = ops.pairwise(Q, X, metric, **kw).cpu().numpy()
+    truth = OM.pairwise_f64(Q, X, metric, **kw)
+    tol = _tol(metric)
+    if metric == "angular_distance" and D == 1:
+        tol = dict(rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(got, truth, **tol)
+
+
+def test_pairwise_golden_reference_vectors(ops, golden_dir):
+    g = np.load(os.path.join(golden_dir, "metrics_golden.npz"))
+    names = {"l1": "l1_distance", "l2": "l2_distance", "linf": "linf_distance",
+             "cosine_similarity": "cosine_similarity", "cosine_distance": "cosine_distance",
+             "magnitude_difference": "magnitude_difference"}
+    for D in (1, 3, 7, 64, 512, 2048):
+        Q, X = g[f"Q_{D}"], g[f"X_{D}"]
+        for m, key in names.items():
+            got = ops.pairwise(Q, X, m).cpu().numpy()
+            np.testing.assert_allclose(got, g[f"{key}_{D}"], rtol=2e-5, atol=1e-5 if m == "magnitude_difference" else 4e-6,
+                                       err_msg=f"{m} D={D}")
+        got = ops.pairwise(Q, X, "l1", normalized=False).cpu().numpy()
+        np.testing.assert_allclose(got, g[f"l1_raw_{D}"], rtol=2e-5)
+        got = ops.pairwise(Q, X, "l2", normalized=False).cpu().numpy()
+        np.testing.assert_allclose(got, g[f"l2_raw_{D}"], rtol=2e-5)
+        got = ops.pairwise(Q, X, "optimized_similarity", params=PARAMS).cpu().numpy()
+        np.testing.assert_allclose(got, g[f"optimized_similarity_{D}"], rtol=1e-4, atol=2e-5)
+        # zero vector: cos -> 0, angle -> pi/2; duplicate: distance exactly 0
+        assert np.all(ops.pairwise(Q, X[:1], "cosine_similarity").cpu().numpy() == 0)
+        np.testing.assert_allclose(ops.pairwise(Q, X[:1], "angular_distance").cpu().numpy(), np.pi / 2, rtol=1e-6)
+        assert ops.pairwise(Q[:1], X[1:2], "l1").item() == 0 and ops.pairwise(Q[:1], X[1:2], "l2").item() == 0
+
+
+# ------------------------------------------------------------------------------- top-k
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("nq,N,D,k", [(1, 1000, 512, 10), (3, 5000, 64, 5), (8, 20000, 128, 100),
+                                      (13, 3001, 100, 10), (40, 777, 36, 1), (2, 300, 2048, 256)])
+def test_topk_fp32_vs_oracle(ops, metric, nq, N, D, k):
+    Q = synth.gaussian(nq, D, 1)
+    X = synth.gaussian(N, D, 2)
+    s, i = ops.topk(Q, X, metric, k)
+    truth = OM.pairwise_f64(Q, X, metric)
+    disputed = check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, k, OM.DESCENDING[metric], **_tol(metric))
+    assert disputed <= max(1, nq * k // 200), f"{disputed} disputed ranks"
+
+
+def test_topk_equals_pairwise_then_stable_sort(ops):
+    """Fused top-k == the same kernel's full matrix + the reference's stable sort, bit for bit."""
+    Q = synth.gaussian(6, 96, 5)
+    X = synth.gaussian(4000, 96, 6)
+    for metric in ("l1", "l2", "linf", "cosine_similarity"):
+        full = ops.pairwise(Q, X, metric).cpu().numpy()
+        tv, ti = OS.topk(full, 20, OM.DESCENDING[metric])
+        s, i = ops.topk(Q, X, metric, 20)
+        assert np.array_equal(i.cpu().numpy(), ti), metric
+        assert np.array_equal(s.cpu().numpy(), tv), metric
+
+
+@pytest.mark.parametrize("metric", ["l1", "l2", "linf"])
+def test_topk_integer_data_exact_with_ties(ops, metric):
+    """Small-integer vectors: every distance is exact in fp32, ties abound -> exact equality with
+    the stable-sort oracle (lower index wins)."""
+    rng = np.random.default_rng(11)
+    X = rng.integers(0, 4, size=(5000, 32)).astype(np.float32)
+    X[100] = X[7]; X[4000] = X[7]; X[4999] = X[7]
+    Q = np.concatenate([X[7:8], rng.integers(0, 4, size=(6, 32)).astype(np.float32)])
+    s, i = ops.topk(Q, X, metric, 50)
+    tv, ti = OS.topk_search(Q, X, metric, 50, dtype=np.float64)
+    assert np.array_equal(i.cpu().numpy(), ti)
+    np.testing.assert_allclose(s.cpu().numpy(), tv, rtol=1e-6)
+    assert list(i[0, :4].cpu().numpy()) == [7, 100, 4000, 4999]
+
+
+def test_topk_edge_cases(ops):
+    import torch
+    Q = synth.gaussian(3, 16, 1)
+    X = synth.gaussian(5, 16, 2)
+    s, i = ops.topk(Q, X, "l2", 8)                       # k > N: padding
+    truth = OM.pairwise_f64(Q, X, "l2")
+    check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 8, False)
+    assert np.all(i[:, 5:].cpu().numpy() == -1) and np.all(np.isposinf(s[:, 5:].cpu().numpy()))
+    s, i = ops.topk(Q, X, "cosine_similarity", 8)
+    assert np.all(np.isneginf(s[:, 5:].cpu().numpy()))
+    s, i = ops.topk(Q, np.zeros((0, 16), np.float32), "l1", 4)     # empty store
+    assert np.all(i.cpu().numpy() == -1)
+    s, i = ops.topk(np.zeros((0, 16), np.float32), X, "l1", 4)     # no queries
+    assert s.shape == (0, 4)
+    s, i = ops.topk(Q, X, "l1", 3, index_offset=1_000_000_000_000)
+    assert np.all(i.cpu().numpy() >= 1_000_000_000_000)
+    Xz = X.copy(); Xz[2] = 0                               # zero row: cos 0 exactly (geometric_metrics.py:16-17)
+    full = ops.pairwise(Q, Xz, "cosine_similarity").cpu().numpy()
+    assert np.all(full[:, 2] == 0)
+    with pytest.raises(ValueError):
+        ops.topk(Q, X, "l1", 0)
+    with pytest.raises(ValueError):
+        ops.topk(Q, X, "l1", 257)
+    with pytest.raises(ValueError):
+        ops.topk(Q, synth.gaussian(5, 17, 3), "l1", 2)
+    # unaligned view (row stride not a multiple of 16 bytes is copied to contiguous by as_device_matrix)
+    big = torch.from_numpy(synth.gaussian(50, 33, 4)).cuda()
+    s, i = ops.topk(big[:2, 1:], big[:, 1:], "l1", 3)
+    truth = OM.pairwise_f64(big[:2, 1:].cpu().numpy(), big[:, 1:].cpu().numpy(), "l1")
+    check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 3, False)
+
+
+def test_abs_score_and_optimized_topk(ops):
+    Q = synth.gaussian(4, 64, 21)
+    X = synth.gaussian(2000, 64, 22)
+    s, i = ops.topk(Q, X, "cosine_similarity", 10, abs_score=True)
+    truth = np.abs(OM.pairwise_f64(Q, X, "cosine_similarity"))
+    check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 10, True, rtol=1e-5, atol=2e-6)
+    s, i = ops.topk(Q, X, "optimized_similarity", 10, params=PARAMS)
+    truth = OM.pairwise_f64(Q, X, "optimized_similarity", params=PARAMS)
+    check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 10, True, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("metric", ["l1", "linf", "l2", "cosine_similarity", "angular_distance"])
+def test_topk_bf16_database(ops, metric):
+    """bf16 rows: the oracle is fed the same bf16-rounded values; arithmetic stays fp32."""
+    import torch
+    Q = OM.bf16_round(synth.gaussian(9, 256, 31, normalize=True))
+    X = OM.bf16_round(synth.gaussian(6000, 256, 32, normalize=True))
+    s, i = ops.topk(torch.from_numpy(Q).bfloat16(), torch.from_numpy(X).bfloat16(), metric, 20,
+                    flags=ops.FLAG_NO_TENSOR)
+    truth = OM.pairwise_f64(Q, X, metric)
+    check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 20, OM.DESCENDING[metric], **_tol(metric))
+
+
+def test_merge_matches_oracle(ops):
+    import torch
+    rng = np.random.default_rng(5)
+    sc = rng.integers(0, 6, size=(16, 4096)).astype(np.float32)      # many ties across shards
+    for desc in (False, True):
+        fv, fi = OS.topk(sc, 33, desc)
+        pv, pi = [], []
+        for r in range(4):
+            v, i = OS.topk(sc[:, r * 1024:(r + 1) * 1024], 33, desc)
+            pv.append(v); pi.append(i + r * 1024)
+        mv, mi = ops.topk_merge(torch.from_numpy(np.stack(pv)).cuda(), torch.from_numpy(np.stack(pi)).cuda(), desc)
+        assert np.array_equal(mi.cpu().numpy(), fi) and np.array_equal(mv.cpu().numpy(), fv)
+    # padded shard lists (idx -1) are ignored
+    v = torch.tensor([[[1.0, np.inf]], [[0.5, 2.0]]]).cuda()
+    i = torch.tensor([[[3, -1]], [[10, 11]]]).cuda()
+    mv, mi = ops.topk_merge(v, i, False)
+    assert mi.cpu().tolist() == [[10, 3]]
+
+
+def test_sharded_equals_single(ops):
+    """Row-sharded search (emulated ranks on one GPU) == single-shard search, exactly."""
+    import torch
+    from image_retrieval_b200.sharded import shard_range
+    Q = synth.gaussian(7, 64, 41)
+    X = synth.gaussian(10007, 64, 42)
+    for metric in ("l1", "cosine_similarity"):
+        s1, i1 = ops.topk(Q, X, metric, 25)
+        for R in (2, 4, 8):
+            ps, pi = [], []
+            for r in range(R):
+                b, e = shard_range(len(X), R, r)
+                s, i = ops.topk(Q, X[b:e], metric, 25, index_offset=b)
+                ps.append(s); pi.append(i)
+            ms, mi = ops.topk_merge(torch.stack(ps), torch.stack(pi), OM.DESCENDING[metric])
+            assert torch.equal(mi, i1) and torch.equal(ms, s1), (metric, R)
+
+
+# ------------------------------------------------------------------------------- histograms
+@pytest.mark.parametrize("cs", ["rgb", "hsv"])
+def test_histogram_bit_exact(ops, cs, golden_dir):
+    g = np.load(os.path.join(golden_dir, "hist_golden.npz"))
+    got = ops.histogram(g["images"], cs).cpu().numpy().astype(np.uint32)
+    assert np.array_equal(got, g[cs])                                   # OpenCV-generated fixture
+    for imgs in (synth.images_uniform(5, 224, 224, 1), synth.images_palette(5, 224, 224, 2),
+                 synth.images_uniform(3, 37, 53, 3),                    # pixel count not a multiple of 16
+                 synth.images_uniform(1, 600, 500, 4)):                 # sliced (multi-CTA) image
+        got = ops.histogram(imgs, cs).cpu().numpy().astype(np.uint32)
+        assert np.array_equal(got, OH.histogram(imgs, cs))
+    flat = np.full((2, 64, 64, 3), 200, np.uint8)                       # worst-case contention
+    assert np.array_equal(ops.histogram(flat, cs).cpu().numpy().astype(np.uint32), OH.histogram(flat, cs))
+
+
+def test_histogram_embedding(ops):
+    imgs = synth.images_palette(6, 64, 64, 9)
+    raw, unit, mag = ops.counts_to_embedding(ops.histogram(imgs))
+    ou, om = OH.embedding(imgs)
+    np.testing.assert_allclose(unit.cpu().numpy(), ou, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(mag.cpu().numpy(), om, rtol=1e-6)
+    assert np.array_equal(raw.cpu().numpy(), OH.histogram(imgs).astype(np.float32))
+
+
+def test_config1_histogram_l2_search(ops):
+    """BASELINE config 1 in miniature: histogram embeddings, L2 top-10 with self matches."""
+    db = synth.images_palette(400, 48, 48, 1002)
+    qi = db[:20]
+    X = ops.counts_to_embedding(ops.histogram(db))[0]
+    Q = ops.counts_to_embedding(ops.histogram(qi))[0]
+    s, i = ops.topk(Q, X, "l2", 10)
+    Xh = OH.histogram(db).astype(np.float32)
+    tv, ti = OS.topk_search(Xh[:20], Xh, "l2", 10, dtype=np.float64)
+    assert np.array_equal(i.cpu().numpy(), ti)                          # integer counts: exact
+    np.testing.assert_allclose(s.cpu().numpy(), tv, rtol=1e-6)
+    assert np.all(i[:, 0].cpu().numpy() == np.arange(20)) and np.all(s[:, 0].cpu().numpy() == 0)

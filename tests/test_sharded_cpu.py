@@ -1,0 +1,78 @@
+"""world_size-2 gloo test of the row-sharded search: shard ranges, index offsets, the single
+all-gather and the merge order.  The local search and the merge are the oracle here (this is a
+CPU test of the host logic; the CUDA operators are covered by -m gpu tests)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from image_retrieval_b200.sharded import ShardedIndex, shard_range
+    from oracle import metrics as OM
+    from oracle import search as OS
+    from oracle import synth
+
+    X = synth.gaussian(1001, 32, 7)
+    X[900] = X[3]                      # tie across shards -> lower global index first
+    Q = np.concatenate([X[3:4], synth.gaussian(4, 32, 8)])
+
+    def local_topk(Qm, Xm, metric, k, index_offset, **kw):
+        v, i = OS.topk_search(Qm, Xm, metric, k, dtype=np.float32)
+        pad = k - v.shape[1]
+        if pad:
+            v = np.pad(v, ((0, 0), (0, pad)), constant_values=np.inf)
+            i = np.pad(i, ((0, 0), (0, pad)), constant_values=-1 - index_offset)
+        return torch.from_numpy(v.astype(np.float32)), torch.from_numpy(i + index_offset)
+
+    def merge(s, i, desc):
+        v, ix = OS.merge_topk(s.numpy(), i.numpy(), s.shape[2], desc)
+        return torch.from_numpy(v), torch.from_numpy(ix)
+
+    b, e = shard_range(len(X), world, rank)
+    index = ShardedIndex(X[b:e], b, local_topk=local_topk, merge=merge)
+    res = {}
+    for metric in ("l1", "cosine_similarity"):
+        s, i = index.topk(Q, metric, 9)
+        res[metric] = (s.numpy(), i.numpy())
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **{f"{m}_{n}": a for m, (s, i) in res.items() for n, a in (("s", s), ("i", i))})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_sharded_search_equals_single(tmp_path):
+    from oracle import search as OS
+    from oracle import synth
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    X = synth.gaussian(1001, 32, 7)
+    X[900] = X[3]
+    Q = np.concatenate([X[3:4], synth.gaussian(4, 32, 8)])
+    r0 = np.load(tmp_path / "rank0.npz")
+    r1 = np.load(tmp_path / "rank1.npz")
+    for metric in ("l1", "cosine_similarity"):
+        v, i = OS.topk_search(Q, X, metric, 9, dtype=np.float32)
+        for r in (r0, r1):
+            assert np.array_equal(r[f"{metric}_i"], i), metric
+            assert np.array_equal(r[f"{metric}_s"], v.astype(np.float32)), metric
+    assert list(r0["l1_i"][0, :2]) == [3, 900]
