@@ -5,8 +5,44 @@
 #include "select.cuh"
 #include "histogram.cuh"
 #include "gemm_topk.h"
+#include "profile.h"
+
+#include <atomic>
+#include <mutex>
+#include <vector>
 
 using namespace b200ir;
+
+namespace b200ir {
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_profile_on{0};
+static std::mutex g_profile_mu;
+struct EventPair { cudaEvent_t a, b; };
+static std::vector<EventPair> g_events[PT_COUNT];
+static cudaEvent_t g_open[PT_COUNT];
+
+void profile_begin(int tag, cudaStream_t st) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_profile_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_profile_mu);
+  if (g_events[tag].size() >= 8192) { g_open[tag] = nullptr; return; }
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) { g_open[tag] = nullptr; return; }
+  cudaEventRecord(e, st);
+  g_open[tag] = e;
+}
+
+void profile_end(int tag, cudaStream_t st) {
+  if (!g_profile_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_profile_mu);
+  if (!g_open[tag]) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) { cudaEventDestroy(g_open[tag]); g_open[tag] = nullptr; return; }
+  cudaEventRecord(e, st);
+  g_events[tag].push_back({g_open[tag], e});
+  g_open[tag] = nullptr;
+}
+}  // namespace b200ir
 
 namespace {
 
@@ -71,6 +107,31 @@ const char* b200ir_error_string(int status) {
   return "b200ir: unknown error";
 }
 
+long long b200ir_launch_count(void) { return g_launches.load(); }
+
+void b200ir_profile_enable(int on) { g_profile_on.store(on ? 1 : 0); }
+
+int b200ir_profile_read(int tag, float* total_ms, int* launches) {
+  if (tag < 0 || tag >= PT_COUNT || !total_ms || !launches) return B200IR_E_ARG;
+  std::lock_guard<std::mutex> lk(g_profile_mu);
+  float sum = 0.f;
+  int n = 0;
+  for (auto& ev : g_events[tag]) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(ev.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ev.a, ev.b);
+    cudaEventDestroy(ev.a);
+    cudaEventDestroy(ev.b);
+    if (e != cudaSuccess) { g_events[tag].clear(); return int(e); }
+    sum += ms;
+    ++n;
+  }
+  g_events[tag].clear();
+  *total_ms = sum;
+  *launches = n;
+  return 0;
+}
+
 int b200ir_device_ok(void) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -86,6 +147,7 @@ int b200ir_row_sqnorms(const void* X, int dtype, int64_t N, int D, float* out, v
   if (reinterpret_cast<uintptr_t>(X) % elem_size(dtype)) return B200IR_E_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = int(ceil_div64(N, 8));
+  ProfileScope ps(PT_MISC, st);
   if (dtype == B200IR_F32) row_sqnorms_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(X), N, D, out);
   else row_sqnorms_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(X), N, D, out);
   return int(cudaGetLastError());
@@ -109,6 +171,7 @@ int b200ir_topk(int metric, int dtype, const void* Q, int64_t nq, const void* X,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (N == 0) {   // empty store: every slot is padding (app_pipeline.py:147-149 returns [])
     const int64_t n = nq * k;
+    ProfileScope ps(PT_MISC, st);
     fill_empty_topk_kernel<<<int(ceil_div64(n, 256)), 256, 0, st>>>(out_score, out_idx, n, metric_descending(metric) ? -INFINITY : INFINITY);
     return int(cudaGetLastError());
   }
@@ -179,6 +242,9 @@ int b200ir_histogram(int colorspace, const uint8_t* img, int64_t B, int H, int W
   if (colorspace == B200IR_HSV) {
     e = init_hsv_tables();
     if (e != cudaSuccess) return int(e);
+  }
+  ProfileScope ps(PT_HIST, st);
+  if (colorspace == B200IR_HSV) {
     histogram_kernel<true><<<unsigned(B * slices), kHistThreads, 0, st>>>(img, pixels, slices, vector_ok, out_counts);
   } else {
     histogram_kernel<false><<<unsigned(B * slices), kHistThreads, 0, st>>>(img, pixels, slices, vector_ok, out_counts);
@@ -191,6 +257,7 @@ int b200ir_counts_to_embedding(const uint32_t* counts, int64_t B, int nb, float*
   if (B < 0 || nb <= 0) return B200IR_E_ARG;
   if (B == 0) return 0;
   if (!counts) return B200IR_E_ARG;
+  ProfileScope ps(PT_MISC, static_cast<cudaStream_t>(stream));
   counts_to_embedding_kernel<<<unsigned(B), 128, 0, static_cast<cudaStream_t>(stream)>>>(counts, nb, raw_out, unit_out, mag_out);
   return int(cudaGetLastError());
 }

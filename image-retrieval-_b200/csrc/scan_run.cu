@@ -1,5 +1,6 @@
 // Scan driver: query preparation + dispatch to the per-(kind, dtype) kernel families.
 #include "scan_topk.cuh"
+#include "profile.h"
 
 namespace b200ir {
 
@@ -7,6 +8,7 @@ cudaError_t launch_prep_queries(int dtype, const void* Q, int nq, int D, int nq_
                                 cudaStream_t st) {
   const int warps_per_block = 8;
   const int blocks = int(ceil_div64(nq_pad, warps_per_block));
+  ProfileScope ps(PT_PREP, st);
   if (dtype == B200IR_F32)
     prep_queries_kernel<float><<<blocks, warps_per_block * 32, 0, st>>>(static_cast<const float*>(Q), nq, D, nq_pad, D_pad, Qf, qn);
   else
@@ -30,6 +32,7 @@ cudaError_t run_scan(const ScanPlan& pl, int dtype, const void* Q, int64_t nq, c
   a.out_all = out_all;
   a.mp = mp;
   const bool f32 = dtype == B200IR_F32;
+  ProfileScope ps(PT_SCAN, st);
   switch (scan_kind_of(mp.metric)) {
     case K_L1:    return f32 ? launch_scan_K_L1_f32(a, pl.TQ, pl.smem, st)    : launch_scan_K_L1_bf16(a, pl.TQ, pl.smem, st);
     case K_L2:    return f32 ? launch_scan_K_L2_f32(a, pl.TQ, pl.smem, st)    : launch_scan_K_L2_bf16(a, pl.TQ, pl.smem, st);

