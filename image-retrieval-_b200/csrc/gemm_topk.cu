@@ -1,11 +1,664 @@
-// tcgen05 / TMEM / TMA path (bring-up stub: path disabled until the kernel lands).
+// tcgen05 / TMEM / TMA path: bf16 cosine-family and L2 top-k as a dense contraction
+// (K1-K4 of SURVEY.md section 2.2) with the top-k selection fused into the accumulator epilogue.
+//
+// Replaces the scan loops of app_pipeline.py:156-172 / :296-328 for bf16 stores: the query batch
+// and the database are the A and B operands (both K-major) of C = Q . X^T.
+//
+//   grid      : one persistent CTA per SM, 256 threads, warp-specialised:
+//                 warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor, 128B-swizzled tiles)
+//                 warp 1 lane 0 : MMA issuer    (tcgen05.mma.cta_group::1.kind::f16, M128 N256 K16)
+//                 warp 2        : TMEM allocator (512 columns = two 128x256 fp32 accumulators)
+//                 warps 4..7    : epilogue, one thread per query row (TMEM lane)
+//   work unit : (128-query tile, contiguous range of 256-row database tiles).  The query tile stays
+//               resident in shared memory (A, up to 128 KB for D = 512) for the whole unit; database
+//               tiles stream through a 3-stage 32 KB ring (B).
+//   epilogue  : tcgen05.ld 32 columns at a time; v = dot * rnorm_x (cosine) or 2 dot - |x|^2 (L2);
+//               a per-thread running threshold rejects almost everything; survivors are appended
+//               to the query's candidate list (L2-resident global scratch) which a warp-wide
+//               bitonic sort compacts to the best k' when it fills.  The distance matrix never
+//               exists in memory.  Each unit emits k' sorted keys per query; a final kernel merges
+//               the partitions, re-ranks the k' candidates with exact fp32 arithmetic on the CUDA
+//               cores (cancellation-free) and writes the k winners.
+#include <cuda.h>
+
 #include "gemm_topk.h"
+#include "profile.h"
 
 namespace b200ir {
 
-bool gemm_path_supported(int, int, int64_t, int64_t, int, int, int) { return false; }
-size_t gemm_workspace_bytes(int, int64_t, int64_t, int, int, int) { return 0; }
-int run_gemm_topk(int, const void*, int64_t, const void*, int64_t, int, int, int64_t, int, const MetricParams&, float*,
-                  int64_t*, unsigned char*, cudaStream_t) { return B200IR_E_SHAPE; }
+namespace gemm {
+
+constexpr int BM = 128;            // queries per tile (UMMA M, TMEM lanes)
+constexpr int BN = 256;            // database rows per tile (UMMA N, TMEM columns per accumulator)
+constexpr int BK = 64;             // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int MAX_KB = 8;          // D <= 512
+constexpr int B_STAGES = 3;
+constexpr int A_KB_BYTES = BM * BK * 2;      // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int SMEM_A = MAX_KB * A_KB_BYTES;  // 128 KB
+constexpr int SMEM_B = B_STAGES * B_STAGE_BYTES;   // 96 KB
+constexpr int SMEM_SCALE = 2 * BN * 4;       // double-buffered per-column scale (rnorm / sqnorm)
+constexpr int SMEM_BARS = 128;
+constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS;   // 231,552 B <= 232,448
+constexpr int THREADS = 256;
+constexpr int TMEM_COLS = 512;
+
+enum Mode { MODE_COS = 0, MODE_ABSCOS = 1, MODE_L2 = 2 };
+
+struct Args {
+  int nq;
+  int64_t N;
+  int D;
+  int num_kb;
+  int num_qtiles;
+  int P;                 // database partitions
+  int tiles_per_part;
+  int total_tiles;
+  int kp;                // candidates kept per (query, partition): k' >= k
+  int cap;               // candidate list capacity (256 or 512)
+  const float* colscale; // [N]: 1/|x| (cosine) or |x|^2 (L2)
+  uint64_t* cand;        // [gridDim.x][128][cap]
+  uint64_t* partial;     // [nq][P][kp]
+};
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
+// start address >> 4 in [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows
+// x 128 B) >> 4 in [32,46), descriptor version 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4,6)=1, A bf16 [7,10)=1, B bf16 [10,13)=1,
+// A/B K-major (bits 15,16 = 0), N>>3 in [17,23), M>>4 in [24,29).
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+
+// ------------------------------------------------------------------------------------ epilogue helpers
+// Warp-cooperative compaction of the candidate lists of the lanes in `mask`: sort, keep the best kp.
+// If `out` is set the sorted list goes to the unit's output slot instead of back to the scratch list.
+template <int E>
+__device__ __noinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp, int& cnt, float& thr, uint32_t mask,
+                                          int lane, uint64_t* out, int64_t out_stride, int valid_lanes) {
+  __syncwarp();
+  while (mask) {
+    const int L = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const int n = __shfl_sync(0xffffffffu, cnt, L);
+    uint64_t* list = warp_lists + size_t(L) * cap;
+    uint64_t r[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = lane * E + e;
+      r[e] = i < n ? list[i] : kKeyInf;
+    }
+    warp_sort<E>(r, lane);
+    if (out == nullptr) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = lane * E + e;
+        if (i < kp) list[i] = r[e];
+      }
+      const int src_lane = (kp - 1) / E, src_e = (kp - 1) % E;
+      uint64_t kth = kKeyInf;
+#pragma unroll
+      for (int e = 0; e < E; ++e) if (e == src_e) kth = r[e];
+      kth = shfl_u64(kth, src_lane);
+      if (lane == L) {
+        cnt = n < kp ? n : kp;
+        if (n >= kp) thr = -key_rank(kth);      // keys hold r = -v: accept only v > thr from now on
+      }
+    } else if (L < valid_lanes) {
+      uint64_t* dst = out + int64_t(L) * out_stride;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = lane * E + e;
+        if (i < kp) dst[i] = r[e];
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int MODE>
+__device__ __forceinline__ float score_of(float dot, float s) {
+  if constexpr (MODE == MODE_COS) return dot * s;
+  else if constexpr (MODE == MODE_ABSCOS) return fabsf(dot) * s;
+  else return fmaf(2.0f, dot, -s);          // -(|x|^2 - 2 q.x): larger = closer
+}
+
+// ------------------------------------------------------------------------------------ main kernel
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + SMEM_A;
+  float* sScale = reinterpret_cast<float*>(smem + SMEM_A + SMEM_B);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_A + SMEM_B + SMEM_SCALE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const uint32_t bar0 = smem_u32(bars);
+  auto B_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto B_EMPTY = [&](int s) { return bar0 + 8u * (3 + s); };
+  const uint32_t A_FULL = bar0 + 8u * 6, A_EMPTY = bar0 + 8u * 7;
+  auto T_FULL = [&](int b) { return bar0 + 8u * (8 + b); };
+  auto T_EMPTY = [&](int b) { return bar0 + 8u * (10 + b); };
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();     // SWIZZLE_128B tiles need 1024-byte alignment
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < B_STAGES; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
+    mbar_init(A_FULL, 1);
+    mbar_init(A_EMPTY, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(T_FULL(b), 1); mbar_init(T_EMPTY(b), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_units = a.num_qtiles * a.P;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      uint32_t kiter = 0, uiter = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uiter) {
+        const int qt = unit % a.num_qtiles, p = unit / a.num_qtiles;
+        mbar_wait(A_EMPTY, (uiter & 1) ^ 1);                   // previous unit's MMAs are done with A
+        mbar_expect_tx(A_FULL, uint32_t(a.num_kb) * A_KB_BYTES);
+        for (int kb = 0; kb < a.num_kb; ++kb) tma_load_2d(smem_u32(sA + kb * A_KB_BYTES), &tmA, A_FULL, kb * BK, qt * BM);
+        const int tile0 = p * a.tiles_per_part;
+        const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
+        for (int t = tile0; t < tile1; ++t) {
+          for (int kb = 0; kb < a.num_kb; ++kb, ++kiter) {
+            const int s = kiter % B_STAGES;
+            const uint32_t ph = (kiter / B_STAGES) & 1;
+            mbar_wait(B_EMPTY(s), ph ^ 1);
+            mbar_expect_tx(B_FULL(s), B_STAGE_BYTES);
+            tma_load_2d(smem_u32(sB + s * B_STAGE_BYTES), &tmB, B_FULL(s), kb * BK, t * BN);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      uint32_t kiter = 0, titer = 0, uiter = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uiter) {
+        const int p = unit / a.num_qtiles;
+        const int tile0 = p * a.tiles_per_part;
+        const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
+        mbar_wait(A_FULL, uiter & 1);
+        tc_fence_after();
+        for (int t = tile0; t < tile1; ++t, ++titer) {
+          const int buf = titer & 1;
+          mbar_wait(T_EMPTY(buf), ((titer >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + uint32_t(buf * BN);
+          for (int kb = 0; kb < a.num_kb; ++kb, ++kiter) {
+            const int s = kiter % B_STAGES;
+            const uint32_t ph = (kiter / B_STAGES) & 1;
+            mbar_wait(B_FULL(s), ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA + kb * A_KB_BYTES);
+            const uint32_t b_addr = smem_u32(sB + s * B_STAGE_BYTES);
+#pragma unroll
+            for (int k4 = 0; k4 < BK / UMMA_K; ++k4) {
+              tc_mma_bf16(tmem_d, make_smem_desc(a_addr + k4 * UMMA_K * 2), make_smem_desc(b_addr + k4 * UMMA_K * 2),
+                          kInstrDesc, (kb | k4) != 0 ? 1u : 0u);
+            }
+            tc_commit(B_EMPTY(s));                              // stage reusable once these MMAs retire
+          }
+          tc_commit(T_FULL(buf));                               // accumulator complete -> epilogue
+        }
+        tc_commit(A_EMPTY);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: one thread per query row =====================
+    const int ewarp = warp - 4;
+    const int row = ewarp * 32 + lane;
+    uint64_t* warp_lists = a.cand + (size_t(blockIdx.x) * BM + ewarp * 32) * a.cap;
+    uint64_t* mylist = warp_lists + size_t(lane) * a.cap;
+    const uint32_t tmem_lane = uint32_t(ewarp * 32) << 16;
+    uint32_t titer = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int qt = unit % a.num_qtiles, p = unit / a.num_qtiles;
+      const int q = qt * BM + row;
+      float thr = q < a.nq ? -INFINITY : INFINITY;             // padding rows of the last query tile accept nothing
+      int cnt = 0;
+      const int tile0 = p * a.tiles_per_part;
+      const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
+      auto load_scale = [&](int t, float& s0, float& s1) {
+        const int64_t c0 = int64_t(t) * BN + row, c1 = c0 + 128;
+        s0 = c0 < a.N ? __ldg(a.colscale + c0) : __int_as_float(0x7fc00000);    // NaN masks rows past N
+        s1 = c1 < a.N ? __ldg(a.colscale + c1) : __int_as_float(0x7fc00000);
+      };
+      {
+        float s0, s1;
+        load_scale(tile0, s0, s1);
+        float* dst = sScale + (titer & 1) * BN;
+        dst[row] = s0;
+        dst[row + 128] = s1;
+      }
+      for (int t = tile0; t < tile1; ++t, ++titer) {
+        const int buf = titer & 1;
+        asm volatile("bar.sync 1, 128;" ::: "memory");         // scale[buf] visible to the 4 epilogue warps
+        float ns0 = 0.f, ns1 = 0.f;
+        const bool has_next = t + 1 < tile1;
+        if (has_next) load_scale(t + 1, ns0, ns1);
+        mbar_wait(T_FULL(buf), (titer >> 1) & 1);
+        tc_fence_after();
+        const float* sc = sScale + buf * BN;
+        const uint32_t base_idx = uint32_t(t) * BN;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t r[32];
+          tc_ld32(tmem_base + tmem_lane + uint32_t(buf * BN + chunk * 32), r);
+          tc_wait_ld();
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(sc + chunk * 32 + c4 * 4);
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float v = score_of<MODE>(__uint_as_float(r[c4 * 4 + j]), sv[j]);
+              if (v > thr) {
+                mylist[cnt] = make_key(-v, base_idx + uint32_t(chunk * 32 + c4 * 4 + j));
+                ++cnt;
+              }
+            }
+          }
+          const uint32_t full = __ballot_sync(0xffffffffu, cnt > a.cap - 32);
+          if (full) {
+            if (a.cap == 256) warp_compact<8>(warp_lists, a.cap, a.kp, cnt, thr, full, lane, nullptr, 0, 32);
+            else warp_compact<16>(warp_lists, a.cap, a.kp, cnt, thr, full, lane, nullptr, 0, 32);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(T_EMPTY(buf));
+        if (has_next) {
+          float* dst = sScale + (buf ^ 1) * BN;
+          dst[row] = ns0;
+          dst[row + 128] = ns1;
+        }
+      }
+      // end of unit: emit the best kp keys of every valid query row of this warp
+      const int q0 = qt * BM + ewarp * 32;
+      const int valid = min(32, a.nq - q0);
+      if (valid > 0) {
+        uint64_t* out = a.partial + (int64_t(q0) * a.P + p) * a.kp;
+        if (a.cap == 256) warp_compact<8>(warp_lists, a.cap, a.kp, cnt, thr, 0xffffffffu, lane, out, int64_t(a.P) * a.kp, valid);
+        else warp_compact<16>(warp_lists, a.cap, a.kp, cnt, thr, 0xffffffffu, lane, out, int64_t(a.P) * a.kp, valid);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ side kernels
+// Per-row scale of the database operand: 1/|x| (0 for a zero row: cos := 0, geometric_metrics.py:16-17) or |x|^2.
+__global__ void row_scale_kernel(const __nv_bfloat16* __restrict__ X, int64_t N, int D, int l2, float* __restrict__ out) {
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const __nv_bfloat16* x = X + row * D;
+  float ss = 0.f;
+  for (int d = lane * 8; d < D; d += 256) {        // D % 8 == 0 on this path
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(x + d));
+    const float f[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) out[row] = l2 ? ss : (ss > 0.f ? 1.0f / sqrtf(ss) : 0.f);
+}
+
+// One warp per query: merge the P partition lists, optionally re-rank the kp candidates with exact fp32
+// arithmetic (direct dot / direct sum of squared differences, fp32, no cancellation), write the k winners.
+template <int E>
+__global__ void __launch_bounds__(128)
+gemm_finalize_kernel(const uint64_t* __restrict__ partial, const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ X,
+                     int nq, int D, int P, int kp, int k, int mode, int rerank, MetricParams mp, int64_t index_offset,
+                     float* __restrict__ out_score, int64_t* __restrict__ out_idx) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const int64_t per_query = int64_t(P) * kp;
+  const uint64_t* src = partial + int64_t(q) * per_query;
+  uint64_t r[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) r[e] = kKeyInf;
+  int kept = 0;
+  int64_t pos = 0;
+  do {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = lane * E + e;
+      if (i >= kept) {
+        const int64_t s = pos + (i - kept);
+        r[e] = s < per_query ? src[s] : kKeyInf;
+      }
+    }
+    pos += 32 * E - kept;
+    warp_sort<E>(r, lane);
+    kept = kp;
+  } while (pos < per_query);
+
+  // query row in registers: lane holds elements [8*(lane + 32 j), +8), j = 0, 1 (D <= 512)
+  const __nv_bfloat16* qrow = Q + int64_t(q) * D;
+  float qf[2][8];
+  float qss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int d = (lane + 32 * j) * 8;
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (d < D) w = __ldg(reinterpret_cast<const uint4*>(qrow + d));
+    qf[j][0] = bf16_lo(w.x); qf[j][1] = bf16_hi(w.x); qf[j][2] = bf16_lo(w.y); qf[j][3] = bf16_hi(w.y);
+    qf[j][4] = bf16_lo(w.z); qf[j][5] = bf16_hi(w.z); qf[j][6] = bf16_lo(w.w); qf[j][7] = bf16_hi(w.w);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qss = fmaf(qf[j][e], qf[j][e], qss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) qss += __shfl_xor_sync(0xffffffffu, qss, o);
+  const float qn = sqrtf(qss);
+
+  const int nl = (kp + E - 1) / E;
+  for (int L = 0; L < nl; ++L) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int c = L * E + e;
+      const uint64_t key = shfl_u64(r[e], L);
+      if (c >= kp || key == kKeyInf) { if (lane == L && c >= kp) r[e] = kKeyInf; continue; }
+      const uint32_t idx = key_index(key);
+      float rank;
+      if (rerank) {
+        const __nv_bfloat16* xrow = X + int64_t(idx) * D;
+        float dot = 0.f, xss = 0.f, d2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int d = (lane + 32 * j) * 8;
+          if (d < D) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(xrow + d));
+            const float xf[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              dot = fmaf(xf[t], qf[j][t], dot);
+              xss = fmaf(xf[t], xf[t], xss);
+              const float df = qf[j][t] - xf[t];
+              d2 = fmaf(df, df, d2);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          dot += __shfl_xor_sync(0xffffffffu, dot, o);
+          xss += __shfl_xor_sync(0xffffffffu, xss, o);
+          d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        }
+        if (mode == MODE_L2) rank = d2;
+        else {
+          const float xn = sqrtf(xss);
+          float cs = (qn != 0.f && xn != 0.f) ? dot / (qn * xn) : 0.f;
+          if (mode == MODE_ABSCOS) cs = fabsf(cs);
+          rank = -cs;
+        }
+      } else {
+        const float v = -key_rank(key);                          // epilogue-domain score
+        if (mode == MODE_L2) rank = fmaxf(qss - v, 0.f);         // |q|^2 + |x|^2 - 2 q.x
+        else rank = -(v * (qn != 0.f ? 1.0f / qn : 0.f));
+      }
+      if (lane == L) r[e] = make_key(rank, idx);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) if (lane * E + e >= kp) r[e] = kKeyInf;
+  warp_sort<E>(r, lane);
+  const bool desc = metric_descending(mp.metric);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    if (i < k) {
+      const uint64_t key = r[e];
+      float sc;
+      int64_t id;
+      if (key == kKeyInf) { sc = desc ? -INFINITY : INFINITY; id = -1; }
+      else { sc = rank_to_score(key_rank(key), mp.metric, mp.flags, mp.D); id = int64_t(key_index(key)) + index_offset; }
+      out_score[int64_t(q) * k + i] = sc;
+      out_idx[int64_t(q) * k + i] = id;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static bool encode_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int D, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {cuuint64_t(D), cuuint64_t(rows)};
+  const cuuint64_t strides[1] = {cuuint64_t(D) * 2};
+  const cuuint32_t box[2] = {cuuint32_t(BK), cuuint32_t(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Plan {
+  int num_qtiles, total_tiles, P, tiles_per_part, kp, cap, grid, num_kb;
+  size_t off_scale, off_cand, off_partial, total_bytes;
+};
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = kNumSMs;
+  }
+  return n;
+}
+
+static Plan make_plan(int64_t nq, int64_t N, int D, int k, int flags, int sms) {
+  Plan pl{};
+  pl.num_kb = (D + BK - 1) / BK;
+  pl.num_qtiles = int(ceil_div64(nq, BM));
+  pl.total_tiles = int(ceil_div64(N, BN));
+  const bool rerank = !(flags & B200IR_FLAG_NO_RERANK);
+  pl.cap = k <= 112 ? 256 : 512;
+  int kp = k;
+  if (rerank) { kp = k + (k / 16 > 4 ? k / 16 : 4); kp = (kp + 3) / 4 * 4; }
+  if (kp > pl.cap / 2) kp = pl.cap / 2;
+  if (kp < k) kp = k;
+  pl.kp = kp;
+  // partitions: minimise rounds x (tiles per unit + fixed per-unit cost), prefer fewer partitions
+  int64_t best_cost = -1;
+  int bestP = 1;
+  const int maxP = pl.total_tiles < 64 ? pl.total_tiles : 64;
+  for (int P = 1; P <= maxP; ++P) {
+    const int tpp = (pl.total_tiles + P - 1) / P;
+    const int Pe = (pl.total_tiles + tpp - 1) / tpp;
+    const int64_t units = int64_t(pl.num_qtiles) * Pe;
+    const int64_t rounds = ceil_div64(units, sms);
+    const int64_t cost = rounds * (tpp + 3);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; bestP = P; }
+  }
+  pl.tiles_per_part = (pl.total_tiles + bestP - 1) / bestP;
+  pl.P = (pl.total_tiles + pl.tiles_per_part - 1) / pl.tiles_per_part;
+  const int64_t units = int64_t(pl.num_qtiles) * pl.P;
+  pl.grid = int(units < sms ? units : sms);
+  size_t off = 0;
+  pl.off_scale = off; off += round_up64(size_t(N) * 4, 256);
+  pl.off_cand = off; off += round_up64(size_t(pl.grid) * BM * pl.cap * 8, 256);
+  pl.off_partial = off; off += round_up64(size_t(nq) * pl.P * pl.kp * 8, 256);
+  pl.total_bytes = off;
+  return pl;
+}
+
+}  // namespace gemm
+
+bool gemm_path_supported(int metric, int dtype, int64_t nq, int64_t N, int D, int k, int flags) {
+  if (dtype != B200IR_BF16) return false;
+  if (!(metric == B200IR_L2 || metric == B200IR_COS_SIM || metric == B200IR_COS_DIST || metric == B200IR_ANGLE)) return false;
+  if (D % 8 != 0 || D > gemm::MAX_KB * gemm::BK || D < 16) return false;
+  if (nq < 32 || N < 4 * gemm::BN) return false;      // tiny problems stay on the scan path
+  if (k > 224) return false;
+  (void)flags;
+  return true;
+}
+
+size_t gemm_workspace_bytes(int metric, int64_t nq, int64_t N, int D, int k, int flags) {
+  (void)metric;
+  int sms = gemm::num_sms();
+  if (sms > kNumSMs) sms = kNumSMs;
+  return gemm::make_plan(nq, N, D, k, flags, sms).total_bytes;
+}
+
+int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t N, int D, int k, int64_t index_offset,
+                  int flags, const MetricParams& mp, float* out_score, int64_t* out_idx, unsigned char* ws, cudaStream_t st) {
+  using namespace gemm;
+  if ((reinterpret_cast<uintptr_t>(Q) & 15) || (reinterpret_cast<uintptr_t>(X) & 15)) return B200IR_E_ALIGN;
+  int sms = num_sms();
+  if (sms > kNumSMs) sms = kNumSMs;
+  const Plan pl = make_plan(nq, N, D, k, flags, sms);
+  const int mode = metric == B200IR_L2 ? MODE_L2 : ((flags & B200IR_FLAG_ABS_SCORE) ? MODE_ABSCOS : MODE_COS);
+
+  CUtensorMap tmA, tmB;
+  if (!encode_bf16_rows(&tmA, Q, nq, D, BM) || !encode_bf16_rows(&tmB, X, N, D, BN)) return B200IR_E_DEVICE;
+
+  float* scale = reinterpret_cast<float*>(ws + pl.off_scale);
+  {
+    ProfileScope ps(PT_PREP, st);
+    row_scale_kernel<<<unsigned(ceil_div64(N, 8)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(X), N, D, mode == MODE_L2 ? 1 : 0, scale);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return int(e);
+  }
+  Args a{};
+  a.nq = int(nq); a.N = N; a.D = D; a.num_kb = pl.num_kb; a.num_qtiles = pl.num_qtiles; a.P = pl.P;
+  a.tiles_per_part = pl.tiles_per_part; a.total_tiles = pl.total_tiles; a.kp = pl.kp; a.cap = pl.cap;
+  a.colscale = scale;
+  a.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
+  a.partial = reinterpret_cast<uint64_t*>(ws + pl.off_partial);
+  {
+    ProfileScope ps(PT_GEMM, st);
+    cudaError_t e;
+    if (mode == MODE_COS) {
+      e = cudaFuncSetAttribute(gemm_topk_kernel<MODE_COS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+      if (e == cudaSuccess) gemm_topk_kernel<MODE_COS><<<pl.grid, THREADS, SMEM_TOTAL, st>>>(tmA, tmB, a);
+    } else if (mode == MODE_ABSCOS) {
+      e = cudaFuncSetAttribute(gemm_topk_kernel<MODE_ABSCOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+      if (e == cudaSuccess) gemm_topk_kernel<MODE_ABSCOS><<<pl.grid, THREADS, SMEM_TOTAL, st>>>(tmA, tmB, a);
+    } else {
+      e = cudaFuncSetAttribute(gemm_topk_kernel<MODE_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+      if (e == cudaSuccess) gemm_topk_kernel<MODE_L2><<<pl.grid, THREADS, SMEM_TOTAL, st>>>(tmA, tmB, a);
+    }
+    if (e != cudaSuccess) return int(e);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return int(e);
+  }
+  {
+    const int rerank = (flags & B200IR_FLAG_NO_RERANK) ? 0 : 1;
+    ProfileScope ps(rerank ? PT_RERANK : PT_FINALIZE, st);
+    const int blocks = int(ceil_div64(nq, 4));
+    const __nv_bfloat16* Qb = static_cast<const __nv_bfloat16*>(Q);
+    const __nv_bfloat16* Xb = static_cast<const __nv_bfloat16*>(X);
+    if (pl.cap == 256)
+      gemm_finalize_kernel<8><<<blocks, 128, 0, st>>>(a.partial, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, out_score, out_idx);
+    else
+      gemm_finalize_kernel<16><<<blocks, 128, 0, st>>>(a.partial, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, out_score, out_idx);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return int(e);
+  }
+  return 0;
+}
 
 }  // namespace b200ir

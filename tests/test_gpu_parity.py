@@ -257,3 +257,81 @@ def test_config1_histogram_l2_search(ops):
     assert np.array_equal(i.cpu().numpy(), ti)                          # integer counts: exact
     np.testing.assert_allclose(s.cpu().numpy(), tv, rtol=1e-6)
     assert np.all(i[:, 0].cpu().numpy() == np.arange(20)) and np.all(s[:, 0].cpu().numpy() == 0)
+
+
+# ------------------------------------------------------------------------------- tcgen05 path
+def _bf16_case(nq, N, D, seed, normalize=True):
+    Q = OM.bf16_round(synth.gaussian(nq, D, seed, normalize=normalize))
+    X = OM.bf16_round(synth.gaussian(N, D, seed + 1, normalize=normalize))
+    return Q, X
+
+
+@pytest.mark.parametrize("metric", ["cosine_similarity", "cosine_distance", "angular_distance", "l2"])
+@pytest.mark.parametrize("nq,N,D,k", [(128, 2048, 512, 10), (200, 5000, 512, 100), (33, 70001, 256, 100),
+                                      (300, 3000, 64, 5), (64, 1500, 136, 200)])
+def test_tensor_path_topk_vs_oracle(ops, metric, nq, N, D, k):
+    """bf16 store on the tcgen05 path (default flags: exact fp32 re-rank of the k' candidates)."""
+    import torch
+    Q, X = _bf16_case(nq, N, D, 50 + D)
+    s, i = ops.topk(torch.from_numpy(Q).bfloat16(), torch.from_numpy(X).bfloat16(), metric, k)
+    truth = OM.pairwise_f64(Q, X, metric)
+    tol = _tol(metric)
+    disputed = check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, k, OM.DESCENDING[metric], **tol)
+    assert disputed <= max(1, nq * k // 200), f"{disputed} disputed ranks"
+
+
+def test_tensor_path_matches_scan_path(ops):
+    """Same inputs through the tcgen05 path and the CUDA-core scan: identical index lists."""
+    import torch
+    Q, X = _bf16_case(150, 9000, 512, 77)
+    Qt, Xt = torch.from_numpy(Q).bfloat16().cuda(), torch.from_numpy(X).bfloat16().cuda()
+    for metric in ("cosine_similarity", "l2"):
+        s1, i1 = ops.topk(Qt, Xt, metric, 50)
+        s2, i2 = ops.topk(Qt, Xt, metric, 50, flags=ops.FLAG_NO_TENSOR)
+        assert (i1 == i2).float().mean().item() > 0.999, metric
+        torch.testing.assert_close(s1, s2, rtol=1e-5, atol=2e-6)
+
+
+def test_tensor_path_near_duplicates_and_no_rerank(ops):
+    """Cancellation case of the |q|^2+|x|^2-2qx form: near-duplicate rows.  The re-rank makes the
+    reported L2 exact; without it the GEMM-form value is only bounded loosely (stated: 1e-2 abs)."""
+    import torch
+    rng = np.random.default_rng(3)
+    Q, X = _bf16_case(64, 4096, 512, 91, normalize=False)
+    X[:64] = Q                                            # exact duplicates of the queries
+    X[64:128] = OM.bf16_round(Q + 0.01 * rng.standard_normal(Q.shape).astype(np.float32))
+    Qt, Xt = torch.from_numpy(Q).bfloat16().cuda(), torch.from_numpy(X).bfloat16().cuda()
+    s, i = ops.topk(Qt, Xt, "l2", 8)
+    truth = OM.pairwise_f64(Q, X, "l2")
+    check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 8, False, rtol=1e-5, atol=1e-30)
+    assert np.all(i[:, 0].cpu().numpy() == np.arange(64)) and np.all(s[:, 0].cpu().numpy() == 0)
+    s2, i2 = ops.topk(Qt, Xt, "l2", 8, flags=ops.FLAG_NO_RERANK)
+    assert np.all(i2[:, 0].cpu().numpy() == np.arange(64))
+    got = s2.cpu().numpy()
+    want = np.take_along_axis(truth, i2.cpu().numpy(), 1)
+    assert np.max(np.abs(got - want)) < 1e-2
+    # zero rows and zero queries keep the reference's cos := 0 convention
+    X[200] = 0
+    Q[5] = 0
+    s, i = ops.topk(torch.from_numpy(Q).bfloat16(), torch.from_numpy(X).bfloat16(), "cosine_similarity", 4096 // 32)
+    truth = OM.pairwise_f64(Q, X, "cosine_similarity")
+    check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 128, True, rtol=1e-5, atol=2e-6)
+    assert np.all(s[5].cpu().numpy() == 0) and list(i[5, :3].cpu().numpy()) == [0, 1, 2]
+
+
+def test_tensor_path_sharded_and_abs(ops):
+    import torch
+    from image_retrieval_b200.sharded import shard_range
+    Q, X = _bf16_case(130, 20000, 512, 17)
+    Qt, Xt = torch.from_numpy(Q).bfloat16().cuda(), torch.from_numpy(X).bfloat16().cuda()
+    s1, i1 = ops.topk(Qt, Xt, "cosine_similarity", 100)
+    ps, pi = [], []
+    for r in range(4):
+        b, e = shard_range(len(X), 4, r)
+        s, i = ops.topk(Qt, Xt[b:e], "cosine_similarity", 100, index_offset=b)
+        ps.append(s); pi.append(i)
+    ms, mi = ops.topk_merge(torch.stack(ps), torch.stack(pi), True)
+    assert torch.equal(mi, i1) and torch.equal(ms, s1)
+    s, i = ops.topk(Qt, Xt, "cosine_similarity", 20, abs_score=True)
+    truth = np.abs(OM.pairwise_f64(Q, X, "cosine_similarity"))
+    check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 20, True, rtol=1e-5, atol=2e-6)
