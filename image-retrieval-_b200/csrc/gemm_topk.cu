@@ -23,6 +23,7 @@
 
 #include "gemm_topk.h"
 #include "profile.h"
+#include "select.cuh"
 
 namespace b200ir {
 
@@ -488,20 +489,7 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const __nv_bfloat16* 
 #pragma unroll
   for (int e = 0; e < E; ++e) if (lane * E + e >= kp) r[e] = kKeyInf;
   warp_sort<E>(r, lane);
-  const bool desc = metric_descending(mp.metric);
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int i = lane * E + e;
-    if (i < k) {
-      const uint64_t key = r[e];
-      float sc;
-      int64_t id;
-      if (key == kKeyInf) { sc = desc ? -INFINITY : INFINITY; id = -1; }
-      else { sc = rank_to_score(key_rank(key), mp.metric, mp.flags, mp.D); id = int64_t(key_index(key)) + index_offset; }
-      out_score[int64_t(q) * k + i] = sc;
-      out_idx[int64_t(q) * k + i] = id;
-    }
-  }
+  emit_topk<E>(r, lane, k, mp, index_offset, out_score, out_idx, int64_t(q));
 }
 
 // ------------------------------------------------------------------------------------ host side

@@ -7,7 +7,7 @@ namespace b200ir {
 enum ScanKind { K_L1 = 0, K_L2 = 1, K_LINF = 2, K_DOT = 3, K_MULTI = 4 };
 
 constexpr int kScanThreads = 128;   // == rows per tile (one row per thread)
-constexpr int kScanStages = 4;
+constexpr int kScanStages = 3;
 constexpr int kRowChunkBytes = 128; // bytes of one row staged per pipeline step
 
 __host__ __device__ inline int scan_kind_of(int metric) {
@@ -61,7 +61,7 @@ inline ScanPlan make_scan_plan(int metric, int dtype, int64_t nq, int64_t N, int
   pl.sortn = pairwise ? 256 : scan_sortn(k);
   pl.smem = size_t(kScanStages) * (kScanThreads * kRowChunkBytes + pl.TQ * DKE * 4)
             + size_t(pl.TQ) * pl.sortn * 8 + pl.TQ * 16;
-  int ctas_per_sm = int((200 * 1024) / pl.smem);
+  int ctas_per_sm = int((227 * 1024) / (pl.smem + 1024));      // 1 KB per resident CTA is reserved by the driver
   ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
   const int64_t target = int64_t(kNumSMs) * ctas_per_sm;
   int64_t P = target / pl.G;

@@ -123,45 +123,59 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
 
   if (tid < TQ) { thr_s[tid] = kKeyInf; cnt_s[tid] = 0; }
 
-  auto issue = [&](int it) {
-    if (it < total) {
-      const int tile = it / nchunks, chunk = it - tile * nchunks;
-      unsigned char* sb = stage_base + (it % kScanStages) * STAGE_BYTES;
-      const int64_t row0 = row_begin + int64_t(tile) * kScanThreads;
-      const int64_t col_byte0 = int64_t(chunk) * kRowChunkBytes;
+  // Loader state advances incrementally (no divisions in the steady state).  Thread t copies the 16-byte
+  // piece c = t & 7 of rows r0 + 16 i (r0 = t >> 3, i = 0..7): (r & 7) == (r0 & 7) for all of them, so the
+  // swizzled destination is one per-thread constant plus i * 2 KB.
+  const int ld_c = tid & 7, ld_r0 = tid >> 3;
+  const uint32_t ld_dst = uint32_t(ld_r0 * kRowChunkBytes + ((ld_c ^ (ld_r0 & 7)) << 4));
+  const unsigned char* ld_src = Xb + (row_begin + ld_r0) * row_bytes + ld_c * 16;
+  const int64_t ld_istride = 16 * row_bytes;
+  const float* ld_q = a.Qf + int64_t(g * TQ + tid / (DKE / 4)) * a.D_pad + (tid % (DKE / 4)) * 4;
+  const uint32_t ld_qdst = uint32_t(XT_BYTES + ((tid / (DKE / 4)) * DKE + (tid % (DKE / 4)) * 4) * 4);
+  int iss_tile = 0, iss_chunk = 0, iss_stage = 0;
+
+  auto issue = [&]() {
+    if (iss_tile < ntiles) {
+      unsigned char* sb = stage_base + iss_stage * STAGE_BYTES;
+      const uint32_t sbu = smem_u32(sb);
+      const int64_t row0 = row_begin + int64_t(iss_tile) * kScanThreads;
+      const int64_t col_byte0 = int64_t(iss_chunk) * kRowChunkBytes;
+      const unsigned char* src0 = ld_src + int64_t(iss_tile) * (kScanThreads * row_bytes) + col_byte0;
+      const bool full = a.aligned && (row0 + kScanThreads <= row_end) && (col_byte0 + kRowChunkBytes <= row_bytes);
+      if (full) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int id = i * kScanThreads + tid;
-        const int r = id >> 3, c = id & 7;
-        const int64_t grow = row0 + r;
-        const int64_t cb = col_byte0 + c * 16;
-        int nbytes = 0;
-        if (grow < row_end) nbytes = int(max(int64_t(0), min(int64_t(16), row_bytes - cb)));
-        const uint32_t dst = smem_u32(sb + r * kRowChunkBytes + ((c ^ (r & 7)) << 4));
-        const unsigned char* src = nbytes > 0 ? Xb + grow * row_bytes + cb : Xb;
-        if (a.aligned) {
-          cp_async_16(dst, src, nbytes);
-        } else {
-          // rows not 16-byte aligned: element loads, staged through registers
-          T tmp[16 / sizeof(T)];
+        for (int i = 0; i < 8; ++i) cp_async_16(sbu + ld_dst + i * 2048, src0 + i * ld_istride, 16);
+      } else {
 #pragma unroll
-          for (int e = 0; e < int(16 / sizeof(T)); ++e)
-            tmp[e] = (int(e * sizeof(T)) < nbytes) ? reinterpret_cast<const T*>(src)[e] : T(0.f);
-          *reinterpret_cast<uint4*>(sb + r * kRowChunkBytes + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<uint4*>(tmp);
+        for (int i = 0; i < 8; ++i) {
+          const int64_t grow = row0 + ld_r0 + 16 * i;
+          const int64_t cb = col_byte0 + ld_c * 16;
+          int nbytes = 0;
+          if (grow < row_end) nbytes = int(max(int64_t(0), min(int64_t(16), row_bytes - cb)));
+          const unsigned char* src = nbytes > 0 ? src0 + i * ld_istride : Xb;
+          if (a.aligned) {
+            cp_async_16(sbu + ld_dst + i * 2048, src, nbytes);
+          } else {
+            // rows not 16-byte aligned: element loads, staged through registers
+            T tmp[16 / sizeof(T)];
+#pragma unroll
+            for (int e = 0; e < int(16 / sizeof(T)); ++e)
+              tmp[e] = (int(e * sizeof(T)) < nbytes) ? reinterpret_cast<const T*>(src)[e] : T(0.f);
+            *reinterpret_cast<uint4*>(sb + ld_dst + i * 2048) = *reinterpret_cast<uint4*>(tmp);
+          }
         }
       }
-      // fp32 query chunk: TQ rows x DKE floats (workspace copy is padded: no guards needed)
-      for (int id = tid; id < TQ * DKE / 4; id += kScanThreads) {
-        const int t = id / (DKE / 4), c = id % (DKE / 4);
-        const float* src = a.Qf + int64_t(g * TQ + t) * a.D_pad + chunk * DKE + c * 4;
-        cp_async_16(smem_u32(sb + XT_BYTES + (t * DKE + c * 4) * 4), src, 16);
-      }
+      // fp32 query chunk: TQ rows x DKE floats (the workspace copy is zero padded: no guards needed)
+      static_assert(TQ * DKE / 4 <= kScanThreads, "query chunk must fit one cp.async per thread");
+      if (tid < TQ * DKE / 4) cp_async_16(sbu + ld_qdst, ld_q + iss_chunk * DKE, 16);
+      if (++iss_chunk == nchunks) { iss_chunk = 0; ++iss_tile; }
+      if (++iss_stage == kScanStages) iss_stage = 0;
     }
     cp_async_commit();
   };
 
 #pragma unroll
-  for (int s = 0; s < kScanStages - 1; ++s) issue(s);
+  for (int s = 0; s < kScanStages - 1; ++s) issue();
 
   float acc[TQ][NA];
   float xsq = 0.f;
@@ -174,12 +188,14 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
 #pragma unroll
   for (int t = 0; t < TQ; ++t) qn[t] = a.qnorm[g * TQ + t];
 
+  int tile = 0, chunk = 0, stage = 0;
   for (int it = 0; it < total; ++it) {
     cp_async_wait<kScanStages - 2>();
     __syncthreads();
-    issue(it + kScanStages - 1);
+    issue();
 
-    const unsigned char* sb = stage_base + (it % kScanStages) * STAGE_BYTES;
+    const unsigned char* sb = stage_base + stage * STAGE_BYTES;
+    if (++stage == kScanStages) stage = 0;
     const unsigned char* xrow = sb + tid * kRowChunkBytes;
     const float* qs = reinterpret_cast<const float*>(sb + XT_BYTES);
 
@@ -230,9 +246,10 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
       for (int j = 0; j < NA; ++j) acc[t][j] = (KIND == K_LINF || j == 3) ? part[t][j] : acc[t][j] + part[t][j];
     xsq += xpart;
 
-    const int tile = it / nchunks, chunk = it - tile * nchunks;
-    if (chunk == nchunks - 1) {
+    if (++chunk == nchunks) {
+      chunk = 0;
       const int64_t grow = row_begin + int64_t(tile) * kScanThreads + tid;
+      ++tile;
       const bool valid = grow < row_end;
 #pragma unroll
       for (int t = 0; t < TQ; ++t) {

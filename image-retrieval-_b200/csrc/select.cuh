@@ -6,6 +6,43 @@
 
 namespace b200ir {
 
+// Final step shared by every top-k path: the first k keys of r[] (sorted by rank value) are turned into the
+// metric's reference-normalised score, then re-sorted by (score, index): transforms such as 1 - cos, sqrt or
+// arccos can round distinct rank values to the same fp32 score, and the reference's stable sort orders equal
+// scores by index (app_pipeline.py:171-172, image_search.py:199-219).
+template <int E>
+__device__ __forceinline__ void emit_topk(uint64_t (&r)[E], int lane, int k, const MetricParams& mp, int64_t index_offset,
+                                          float* __restrict__ out_score, int64_t* __restrict__ out_idx, int64_t q) {
+  const bool desc = metric_descending(mp.metric);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    if (i < k && r[e] != kKeyInf) {
+      const float sc = rank_to_score(key_rank(r[e]), mp.metric, mp.flags, mp.D);
+      r[e] = make_key(desc ? -sc : sc, key_index(r[e]));
+    } else {
+      r[e] = kKeyInf;
+    }
+  }
+  warp_sort<E>(r, lane);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    if (i < k) {
+      float sc;
+      int64_t id;
+      if (r[e] == kKeyInf) { sc = desc ? -INFINITY : INFINITY; id = -1; }
+      else {
+        const float v = key_rank(r[e]);
+        sc = desc ? 0.0f - v : v;
+        id = int64_t(key_index(r[e])) + index_offset;
+      }
+      out_score[q * k + i] = sc;
+      out_idx[q * k + i] = id;
+    }
+  }
+}
+
 // One warp per query: stream P*k sorted-or-not keys through a 32*E-wide bitonic sorter, keeping
 // the best k between rounds.  Writes the reference-normalised score and the global index.
 template <int E>
@@ -34,20 +71,7 @@ __global__ void __launch_bounds__(128) finalize_topk_kernel(const uint64_t* __re
     warp_sort<E>(r, lane);
     kept = k;
   } while (pos < per_query);
-  const bool desc = metric_descending(mp.metric);
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int i = lane * E + e;
-    if (i < k) {
-      const uint64_t key = r[e];
-      float sc;
-      int64_t id;
-      if (key == kKeyInf) { sc = desc ? -INFINITY : INFINITY; id = -1; }
-      else { sc = rank_to_score(key_rank(key), mp.metric, mp.flags, mp.D); id = int64_t(key_index(key)) + index_offset; }
-      out_score[int64_t(q) * k + i] = sc;
-      out_idx[int64_t(q) * k + i] = id;
-    }
-  }
+  emit_topk<E>(r, lane, k, mp, index_offset, out_score, out_idx, int64_t(q));
 }
 
 // Cross-shard merge: score/idx [R, nq, k] -> [nq, k] ordered by (score, global idx).
