@@ -11,6 +11,8 @@ uint8 image (embedded with the colour-histogram kernel) or - if a `text_encoder`
 given - a string.
 """
 import logging
+import os
+from pathlib import Path
 
 import numpy as np
 import torch
@@ -105,10 +107,53 @@ class EnhancedImageSearchApp:
             self._embeddings[str(p)] = v
         return len(paths)
 
-    def process_images(self, image_paths, colorspace="rgb"):
-        """Reference: load CLIP embeddings (app_pipeline.py:29-90).  Here: colour-histogram embeddings
-        of the image files (PIL decode on the host, histogram on the device); unreadable files are
-        skipped with a warning, like the reference's per-image try/except."""
+    # the reference's on-disk cache format: np.savez(file, embeddings={path: vector}) (a pickled dict,
+    # color_analysis_workflow.py:145, app_pipeline.py:124), searched for at these places (app_pipeline.py:34-42)
+    EMBEDDING_CACHE_PATHS = (
+        "color_embeddings.npz", "color_analysis/color_embeddings.npz", "../color_embeddings.npz", "embeddings.npz",
+        "color_dataset/embeddings.npz", os.path.expanduser("~/Desktop/color_embeddings.npz"),
+        os.path.expanduser("~/Desktop/color_analysis/color_embeddings.npz"))
+
+    @staticmethod
+    def load_embeddings_npz(path):
+        """{path: vector} dict from the reference's .npz cache (app_pipeline.py:54-58, mi_analysis.py:239-248)."""
+        data = np.load(path, allow_pickle=True)
+        if 'embeddings' not in data:
+            raise KeyError(f"{path} has no 'embeddings' entry")
+        return data['embeddings'].item()
+
+    def save_embeddings_npz(self, path):
+        """Write the store in the reference's cache format (app_pipeline.py:124)."""
+        np.savez(path, embeddings=dict(self._embeddings.items()))
+
+    def process_images(self, image_paths, colorspace="rgb", embeddings_file=None):
+        """app_pipeline.py:29-90: adopt pre-computed embeddings from an .npz cache when one matches the selected
+        images (exact path first, then file name), else compute embeddings - here colour-histogram embeddings of
+        the image files (PIL decode on the host, histogram on the device; CLIP is out of scope).  Unreadable
+        files are skipped with a warning, like the reference's per-image try/except."""
+        logger.info(f"Processing {len(image_paths)} images...")
+        candidates = [embeddings_file] if embeddings_file else list(self.EMBEDDING_CACHE_PATHS)
+        cache = next((c for c in candidates if c and os.path.exists(c)), None)
+        if cache:
+            try:
+                stored = self.load_embeddings_npz(cache)
+                by_name = {}
+                for sp in stored:
+                    by_name.setdefault(Path(sp).name, sp)          # first stored path wins, as in the reference loop
+                matched = {}
+                for image_path in image_paths:
+                    sp = str(image_path)
+                    if sp in stored:
+                        matched[sp] = stored[sp]
+                    elif Path(image_path).name in by_name:
+                        matched[sp] = stored[by_name[Path(image_path).name]]
+                if matched:
+                    self._embeddings.update(matched)
+                    logger.info(f"Successfully matched {len(matched)}/{len(image_paths)} images with embeddings")
+                    return len(matched)
+                logger.warning("No matching embeddings found for selected images")
+            except Exception as e:  # noqa: BLE001 - mirror of the reference's broad handler
+                logger.warning(f"Failed to load pre-computed embeddings: {e}")
         from PIL import Image
         done = 0
         for path in image_paths:
@@ -116,7 +161,7 @@ class EnhancedImageSearchApp:
                 with Image.open(path) as im:
                     arr = np.asarray(im.convert("RGB"), dtype=np.uint8)
                 done += self.process_image_arrays([path], arr[None], colorspace)
-            except Exception as e:  # noqa: BLE001 - mirror of the reference's broad handler
+            except Exception as e:  # noqa: BLE001
                 logger.warning(f"Skipping {path} due to error: {e}")
         return done
 

@@ -58,9 +58,10 @@ struct Args {
   int total_tiles;
   int kp;                // candidates kept per (query, partition): k' >= k
   int cap;               // candidate list capacity (256 or 512)
-  const float* colscale; // [N]: 1/|x| (cosine) or |x|^2 (L2)
+  const float* colscale; // [total_tiles*256]: 1/|x| (cosine) or |x|^2 (L2), NaN past row N
   uint64_t* cand;        // [gridDim.x][128][cap]
   uint64_t* partial;     // [nq][P][kp]
+  uint32_t* thr_g;       // [num_qtiles*128] best published k'-th rank value per query (ordered bits), 0xffffffff = none
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -87,6 +88,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -130,9 +135,20 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(B
 // ------------------------------------------------------------------------------------ epilogue helpers
 // Warp-cooperative compaction of the candidate lists of the lanes in `mask`: sort, keep the best kp.
 // If `out` is set the sorted list goes to the unit's output slot instead of back to the scratch list.
+// Cross-unit threshold sharing: after a compaction the k'-th best rank value of a query is published with
+// atomicMin; any unit working on the same query may discard candidates that are strictly worse (at least k'
+// better rows exist somewhere).  Imported thresholds are non-strict (equal scores may still win on index).
+__device__ __forceinline__ void import_threshold(const uint32_t* thr_g_q, float& thr) {
+  const uint32_t g = *reinterpret_cast<const volatile uint32_t*>(thr_g_q);
+  if (g != 0xffffffffu) {
+    const float gv = -ordered_to_f32(g);
+    thr = fmaxf(thr, nextafterf(gv, -INFINITY));
+  }
+}
+
 template <int E>
 __device__ __noinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp, int& cnt, float& thr, uint32_t mask,
-                                          int lane, uint64_t* out, int64_t out_stride, int valid_lanes) {
+                                          int lane, uint64_t* out, int64_t out_stride, int valid_lanes, uint32_t* thr_g_warp) {
   __syncwarp();
   while (mask) {
     const int L = __ffs(mask) - 1;
@@ -159,7 +175,11 @@ __device__ __noinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp,
       kth = shfl_u64(kth, src_lane);
       if (lane == L) {
         cnt = n < kp ? n : kp;
-        if (n >= kp) thr = -key_rank(kth);      // keys hold r = -v: accept only v > thr from now on
+        if (n >= kp) {
+          thr = fmaxf(thr, -key_rank(kth));     // keys hold r = -v: accept only v > thr from now on
+          atomicMin(thr_g_warp + L, uint32_t(kth >> 32));
+          import_threshold(thr_g_warp + L, thr);
+        }
       }
     } else if (L < valid_lanes) {
       uint64_t* dst = out + int64_t(L) * out_stride;
@@ -171,6 +191,12 @@ __device__ __noinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp,
     }
   }
   __syncwarp();
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));     // sm_100 3-input max; NaN inputs are skipped
+  return d;
 }
 
 template <int MODE>
@@ -189,7 +215,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sB = smem + SMEM_A;
   float* sScale = reinterpret_cast<float*>(smem + SMEM_A + SMEM_B);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_A + SMEM_B + SMEM_SCALE);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const uint32_t bar0 = smem_u32(bars);
   auto B_FULL = [&](int s) { return bar0 + 8u * s; };
@@ -197,6 +223,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t A_FULL = bar0 + 8u * 6, A_EMPTY = bar0 + 8u * 7;
   auto T_FULL = [&](int b) { return bar0 + 8u * (8 + b); };
   auto T_EMPTY = [&](int b) { return bar0 + 8u * (10 + b); };
+  auto S_FULL = [&](int b) { return bar0 + 8u * (12 + b); };
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -211,7 +238,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < B_STAGES; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
     mbar_init(A_FULL, 1);
     mbar_init(A_EMPTY, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(T_FULL(b), 1); mbar_init(T_EMPTY(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(T_FULL(b), 1); mbar_init(T_EMPTY(b), 4); mbar_init(S_FULL(b), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -228,7 +255,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      uint32_t kiter = 0, uiter = 0;
+      uint32_t kiter = 0, uiter = 0, titer = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uiter) {
         const int qt = unit % a.num_qtiles, p = unit / a.num_qtiles;
         mbar_wait(A_EMPTY, (uiter & 1) ^ 1);                   // previous unit's MMAs are done with A
@@ -236,7 +263,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < a.num_kb; ++kb) tma_load_2d(smem_u32(sA + kb * A_KB_BYTES), &tmA, A_FULL, kb * BK, qt * BM);
         const int tile0 = p * a.tiles_per_part;
         const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
-        for (int t = tile0; t < tile1; ++t) {
+        for (int t = tile0; t < tile1; ++t, ++titer) {
           for (int kb = 0; kb < a.num_kb; ++kb, ++kiter) {
             const int s = kiter % B_STAGES;
             const uint32_t ph = (kiter / B_STAGES) & 1;
@@ -244,6 +271,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_expect_tx(B_FULL(s), B_STAGE_BYTES);
             tma_load_2d(smem_u32(sB + s * B_STAGE_BYTES), &tmB, B_FULL(s), kb * BK, t * BN);
           }
+          // per-column scale of this tile: its buffer is free once the epilogue released accumulator `buf`
+          // two tiles ago (already true by now in steady state: the MMAs of this tile are running)
+          const int buf = titer & 1;
+          mbar_wait(T_EMPTY(buf), ((titer >> 1) & 1) ^ 1);
+          mbar_expect_tx(S_FULL(buf), BN * 4);
+          bulk_load_1d(smem_u32(sScale + buf * BN), a.colscale + int64_t(t) * BN, BN * 4, S_FULL(buf));
         }
       }
     }
@@ -296,24 +329,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int cnt = 0;
       const int tile0 = p * a.tiles_per_part;
       const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
-      auto load_scale = [&](int t, float& s0, float& s1) {
-        const int64_t c0 = int64_t(t) * BN + row, c1 = c0 + 128;
-        s0 = c0 < a.N ? __ldg(a.colscale + c0) : __int_as_float(0x7fc00000);    // NaN masks rows past N
-        s1 = c1 < a.N ? __ldg(a.colscale + c1) : __int_as_float(0x7fc00000);
-      };
-      {
-        float s0, s1;
-        load_scale(tile0, s0, s1);
-        float* dst = sScale + (titer & 1) * BN;
-        dst[row] = s0;
-        dst[row + 128] = s1;
-      }
+      uint32_t* thr_g_warp = a.thr_g + qt * BM + ewarp * 32;
+      import_threshold(thr_g_warp + lane, thr);
       for (int t = tile0; t < tile1; ++t, ++titer) {
         const int buf = titer & 1;
-        asm volatile("bar.sync 1, 128;" ::: "memory");         // scale[buf] visible to the 4 epilogue warps
-        float ns0 = 0.f, ns1 = 0.f;
-        const bool has_next = t + 1 < tile1;
-        if (has_next) load_scale(t + 1, ns0, ns1);
+        if (((t - tile0) & 15) == 15) import_threshold(thr_g_warp + lane, thr);
+        mbar_wait(S_FULL(buf), (titer >> 1) & 1);
         mbar_wait(T_FULL(buf), (titer >> 1) & 1);
         tc_fence_after();
         const float* sc = sScale + buf * BN;
@@ -323,41 +344,49 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[32];
           tc_ld32(tmem_base + tmem_lane + uint32_t(buf * BN + chunk * 32), r);
           tc_wait_ld();
+          // branch-free pre-filter: score all 32 columns, reduce with 3-input max (NaN = masked column is
+          // ignored by max.f32), and only a thread whose chunk maximum beats its threshold walks the chunk
+          float v[32];
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const float4 s4 = *reinterpret_cast<const float4*>(sc + chunk * 32 + c4 * 4);
-            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+            v[c4 * 4 + 0] = score_of<MODE>(__uint_as_float(r[c4 * 4 + 0]), s4.x);
+            v[c4 * 4 + 1] = score_of<MODE>(__uint_as_float(r[c4 * 4 + 1]), s4.y);
+            v[c4 * 4 + 2] = score_of<MODE>(__uint_as_float(r[c4 * 4 + 2]), s4.z);
+            v[c4 * 4 + 3] = score_of<MODE>(__uint_as_float(r[c4 * 4 + 3]), s4.w);
+          }
+          float m[11];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float v = score_of<MODE>(__uint_as_float(r[c4 * 4 + j]), sv[j]);
-              if (v > thr) {
-                mylist[cnt] = make_key(-v, base_idx + uint32_t(chunk * 32 + c4 * 4 + j));
+          for (int i = 0; i < 10; ++i) m[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+          m[10] = fmaxf(v[30], v[31]);
+          const float m0 = fmax3(m[0], m[1], m[2]), m1 = fmax3(m[3], m[4], m[5]), m2 = fmax3(m[6], m[7], m[8]);
+          const float mx = fmax3(fmax3(m0, m1, m2), m[9], m[10]);
+          if (mx > thr) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              if (v[c] > thr) {
+                mylist[cnt] = make_key(-v[c], base_idx + uint32_t(chunk * 32 + c));
                 ++cnt;
               }
             }
           }
           const uint32_t full = __ballot_sync(0xffffffffu, cnt > a.cap - 32);
           if (full) {
-            if (a.cap == 256) warp_compact<8>(warp_lists, a.cap, a.kp, cnt, thr, full, lane, nullptr, 0, 32);
-            else warp_compact<16>(warp_lists, a.cap, a.kp, cnt, thr, full, lane, nullptr, 0, 32);
+            if (a.cap == 256) warp_compact<8>(warp_lists, a.cap, a.kp, cnt, thr, full, lane, nullptr, 0, 32, thr_g_warp);
+            else warp_compact<16>(warp_lists, a.cap, a.kp, cnt, thr, full, lane, nullptr, 0, 32, thr_g_warp);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(T_EMPTY(buf));
-        if (has_next) {
-          float* dst = sScale + (buf ^ 1) * BN;
-          dst[row] = ns0;
-          dst[row + 128] = ns1;
-        }
       }
       // end of unit: emit the best kp keys of every valid query row of this warp
       const int q0 = qt * BM + ewarp * 32;
       const int valid = min(32, a.nq - q0);
       if (valid > 0) {
         uint64_t* out = a.partial + (int64_t(q0) * a.P + p) * a.kp;
-        if (a.cap == 256) warp_compact<8>(warp_lists, a.cap, a.kp, cnt, thr, 0xffffffffu, lane, out, int64_t(a.P) * a.kp, valid);
-        else warp_compact<16>(warp_lists, a.cap, a.kp, cnt, thr, 0xffffffffu, lane, out, int64_t(a.P) * a.kp, valid);
+        if (a.cap == 256) warp_compact<8>(warp_lists, a.cap, a.kp, cnt, thr, 0xffffffffu, lane, out, int64_t(a.P) * a.kp, valid, thr_g_warp);
+        else warp_compact<16>(warp_lists, a.cap, a.kp, cnt, thr, 0xffffffffu, lane, out, int64_t(a.P) * a.kp, valid, thr_g_warp);
       }
     }
   }
@@ -372,10 +401,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 // ------------------------------------------------------------------------------------ side kernels
 // Per-row scale of the database operand: 1/|x| (0 for a zero row: cos := 0, geometric_metrics.py:16-17) or |x|^2.
-__global__ void row_scale_kernel(const __nv_bfloat16* __restrict__ X, int64_t N, int D, int l2, float* __restrict__ out) {
+__global__ void row_scale_kernel(const __nv_bfloat16* __restrict__ X, int64_t N, int64_t N_pad, int D, int l2, float* __restrict__ out) {
   const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (row >= N) return;
+  if (row >= N_pad) return;
+  if (row >= N) { if (lane == 0) out[row] = __int_as_float(0x7fc00000); return; }    // NaN masks rows past N
   const __nv_bfloat16* x = X + row * D;
   float ss = 0.f;
   for (int d = lane * 8; d < D; d += 256) {        // D % 8 == 0 on this path
@@ -523,7 +553,7 @@ static bool encode_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, i
 
 struct Plan {
   int num_qtiles, total_tiles, P, tiles_per_part, kp, cap, grid, num_kb;
-  size_t off_scale, off_cand, off_partial, total_bytes;
+  size_t off_scale, off_thr, off_cand, off_partial, total_bytes;
 };
 
 static int num_sms() {
@@ -565,7 +595,8 @@ static Plan make_plan(int64_t nq, int64_t N, int D, int k, int flags, int sms) {
   const int64_t units = int64_t(pl.num_qtiles) * pl.P;
   pl.grid = int(units < sms ? units : sms);
   size_t off = 0;
-  pl.off_scale = off; off += round_up64(size_t(N) * 4, 256);
+  pl.off_scale = off; off += round_up64(size_t(pl.total_tiles) * BN * 4, 256);
+  pl.off_thr = off; off += round_up64(size_t(pl.num_qtiles) * BM * 4, 256);
   pl.off_cand = off; off += round_up64(size_t(pl.grid) * BM * pl.cap * 8, 256);
   pl.off_partial = off; off += round_up64(size_t(nq) * pl.P * pl.kp * 8, 256);
   pl.total_bytes = off;
@@ -606,7 +637,10 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
   float* scale = reinterpret_cast<float*>(ws + pl.off_scale);
   {
     ProfileScope ps(PT_PREP, st);
-    row_scale_kernel<<<unsigned(ceil_div64(N, 8)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(X), N, D, mode == MODE_L2 ? 1 : 0, scale);
+    const int64_t N_pad = int64_t(pl.total_tiles) * BN;
+    row_scale_kernel<<<unsigned(ceil_div64(N_pad, 8)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(X), N, N_pad, D, mode == MODE_L2 ? 1 : 0, scale);
+    cudaError_t em = cudaMemsetAsync(ws + pl.off_thr, 0xff, size_t(pl.num_qtiles) * BM * 4, st);
+    if (em != cudaSuccess) return int(em);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return int(e);
   }
@@ -616,6 +650,7 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
   a.colscale = scale;
   a.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
   a.partial = reinterpret_cast<uint64_t*>(ws + pl.off_partial);
+  a.thr_g = reinterpret_cast<uint32_t*>(ws + pl.off_thr);
   {
     ProfileScope ps(PT_GEMM, st);
     cudaError_t e;

@@ -102,3 +102,19 @@ def test_surface_names_match_reference():
     app = EnhancedImageSearchApp()
     assert app.search_images(np.ones(512)) == []
     assert app.search_with_multiple_metrics(np.ones(512)) == {'analysis': {'intersections': {}, 'unique_contributions': {}}}
+
+
+def test_npz_cache_roundtrip_without_gpu(tmp_path):
+    """The reference's .npz dict cache (app_pipeline.py:34-58) is adopted by path, then by file name."""
+    from image_retrieval_b200.app_pipeline import EnhancedImageSearchApp
+    stored = {"/data/a/img1.jpg": np.arange(4, dtype=np.float32), "/data/a/img2.jpg": np.ones(4, np.float32)}
+    f = tmp_path / "embeddings.npz"
+    np.savez(f, embeddings=stored)
+    assert set(EnhancedImageSearchApp.load_embeddings_npz(f)) == set(stored)
+    app = EnhancedImageSearchApp()
+    n = app.process_images(["/data/a/img1.jpg", "/elsewhere/img2.jpg"], embeddings_file=str(f))
+    assert n == 2 and list(app.embeddings) == ["/data/a/img1.jpg", "/elsewhere/img2.jpg"]
+    assert np.array_equal(app.embeddings["/elsewhere/img2.jpg"], stored["/data/a/img2.jpg"])
+    out = tmp_path / "out.npz"
+    app.save_embeddings_npz(out)
+    assert set(EnhancedImageSearchApp.load_embeddings_npz(out)) == set(app.embeddings)
