@@ -20,6 +20,8 @@
 //               the partitions, re-ranks the k' candidates with exact fp32 arithmetic on the CUDA
 //               cores (cancellation-free) and writes the k winners.
 #include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
 
 #include "gemm_topk.h"
 #include "profile.h"
@@ -62,7 +64,11 @@ struct Args {
   uint64_t* cand;        // [gridDim.x][128][cap]
   uint64_t* partial;     // [nq][P][kp]
   uint32_t* thr_g;       // [num_qtiles*128] best published k'-th rank value per query (ordered bits), 0xffffffff = none
+  unsigned long long* dbg;   // optional [gridDim.x][16] cycle counters (B200IR_GEMM_DEBUG=1), else nullptr
 };
+
+#define DBG_T0() (a.dbg ? clock64() : 0ll)
+#define DBG_ADD(slot, t0) do { if (a.dbg) a.dbg[blockIdx.x * 16 + (slot)] += (unsigned long long)(clock64() - (t0)); } while (0)
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -146,9 +152,11 @@ __device__ __forceinline__ void import_threshold(const uint32_t* thr_g_q, float&
   }
 }
 
+struct ListState { int cnt; float thr; };     // returned by value: both stay in registers in the caller
+
 template <int E>
-__device__ __noinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp, int& cnt, float& thr, uint32_t mask,
-                                          int lane, uint64_t* out, int64_t out_stride, int valid_lanes, uint32_t* thr_g_warp) {
+__device__ __noinline__ ListState warp_compact(uint64_t* warp_lists, int cap, int kp, int cnt, float thr, uint32_t mask,
+                                               int lane, uint64_t* out, int64_t out_stride, int valid_lanes, uint32_t* thr_g_warp) {
   __syncwarp();
   while (mask) {
     const int L = __ffs(mask) - 1;
@@ -191,6 +199,7 @@ __device__ __noinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp,
     }
   }
   __syncwarp();
+  return ListState{cnt, thr};
 }
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -258,7 +267,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t kiter = 0, uiter = 0, titer = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uiter) {
         const int qt = unit % a.num_qtiles, p = unit / a.num_qtiles;
+        long long t0 = DBG_T0();
         mbar_wait(A_EMPTY, (uiter & 1) ^ 1);                   // previous unit's MMAs are done with A
+        DBG_ADD(1, t0);
         mbar_expect_tx(A_FULL, uint32_t(a.num_kb) * A_KB_BYTES);
         for (int kb = 0; kb < a.num_kb; ++kb) tma_load_2d(smem_u32(sA + kb * A_KB_BYTES), &tmA, A_FULL, kb * BK, qt * BM);
         const int tile0 = p * a.tiles_per_part;
@@ -267,14 +278,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int kb = 0; kb < a.num_kb; ++kb, ++kiter) {
             const int s = kiter % B_STAGES;
             const uint32_t ph = (kiter / B_STAGES) & 1;
+            t0 = DBG_T0();
             mbar_wait(B_EMPTY(s), ph ^ 1);
+            DBG_ADD(0, t0);
             mbar_expect_tx(B_FULL(s), B_STAGE_BYTES);
             tma_load_2d(smem_u32(sB + s * B_STAGE_BYTES), &tmB, B_FULL(s), kb * BK, t * BN);
           }
           // per-column scale of this tile: its buffer is free once the epilogue released accumulator `buf`
           // two tiles ago (already true by now in steady state: the MMAs of this tile are running)
           const int buf = titer & 1;
+          t0 = DBG_T0();
           mbar_wait(T_EMPTY(buf), ((titer >> 1) & 1) ^ 1);
+          DBG_ADD(2, t0);
           mbar_expect_tx(S_FULL(buf), BN * 4);
           bulk_load_1d(smem_u32(sScale + buf * BN), a.colscale + int64_t(t) * BN, BN * 4, S_FULL(buf));
         }
@@ -288,17 +303,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int p = unit / a.num_qtiles;
         const int tile0 = p * a.tiles_per_part;
         const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
+        long long t0 = DBG_T0();
         mbar_wait(A_FULL, uiter & 1);
+        DBG_ADD(5, t0);
         tc_fence_after();
         for (int t = tile0; t < tile1; ++t, ++titer) {
           const int buf = titer & 1;
+          t0 = DBG_T0();
           mbar_wait(T_EMPTY(buf), ((titer >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+          DBG_ADD(4, t0);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + uint32_t(buf * BN);
           for (int kb = 0; kb < a.num_kb; ++kb, ++kiter) {
             const int s = kiter % B_STAGES;
             const uint32_t ph = (kiter / B_STAGES) & 1;
+            t0 = DBG_T0();
             mbar_wait(B_FULL(s), ph);
+            DBG_ADD(3, t0);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(sA + kb * A_KB_BYTES);
             const uint32_t b_addr = smem_u32(sB + s * B_STAGE_BYTES);
@@ -334,18 +355,21 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int t = tile0; t < tile1; ++t, ++titer) {
         const int buf = titer & 1;
         if (((t - tile0) & 15) == 15) import_threshold(thr_g_warp + lane, thr);
+        const bool dbg_me = a.dbg && ewarp == 0 && lane == 0;
+        long long t0 = dbg_me ? clock64() : 0ll;
         mbar_wait(S_FULL(buf), (titer >> 1) & 1);
         mbar_wait(T_FULL(buf), (titer >> 1) & 1);
+        if (dbg_me) { a.dbg[blockIdx.x * 16 + 7] += (unsigned long long)(clock64() - t0); t0 = clock64(); }
+        long long tcomp = 0;
         tc_fence_after();
         const float* sc = sScale + buf * BN;
         const uint32_t base_idx = uint32_t(t) * BN;
-#pragma unroll 1
-        for (int chunk = 0; chunk < BN / 32; ++chunk) {
-          uint32_t r[32];
-          tc_ld32(tmem_base + tmem_lane + uint32_t(buf * BN + chunk * 32), r);
-          tc_wait_ld();
-          // branch-free pre-filter: score all 32 columns, reduce with 3-input max (NaN = masked column is
-          // ignored by max.f32), and only a thread whose chunk maximum beats its threshold walks the chunk
+        // 8 chunks of 32 columns, software-pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is
+        // scored (register double buffer rA / rB).
+        auto process = [&](uint32_t (&r)[32], int chunk) {
+          // branch-free pre-filter: score all 32 columns and reduce with 3-input max (max.f32 skips NaN = masked
+          // columns).  Only a thread whose 8-column group maximum beats its threshold touches that group, and it
+          // extracts the hits by arg-max (select chains, no per-element branches).
           float v[32];
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
@@ -355,32 +379,66 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[c4 * 4 + 2] = score_of<MODE>(__uint_as_float(r[c4 * 4 + 2]), s4.z);
             v[c4 * 4 + 3] = score_of<MODE>(__uint_as_float(r[c4 * 4 + 3]), s4.w);
           }
-          float m[11];
+          float gm[4];
 #pragma unroll
-          for (int i = 0; i < 10; ++i) m[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
-          m[10] = fmaxf(v[30], v[31]);
-          const float m0 = fmax3(m[0], m[1], m[2]), m1 = fmax3(m[3], m[4], m[5]), m2 = fmax3(m[6], m[7], m[8]);
-          const float mx = fmax3(fmax3(m0, m1, m2), m[9], m[10]);
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const float* w = v + g8 * 8;
+            gm[g8] = fmax3(fmax3(w[0], w[1], w[2]), fmax3(w[3], w[4], w[5]), fmaxf(w[6], w[7]));
+          }
+          const float mx = fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]);
           if (mx > thr) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              if (v[c] > thr) {
-                mylist[cnt] = make_key(-v[c], base_idx + uint32_t(chunk * 32 + c));
+            for (int g8 = 0; g8 < 4; ++g8) {
+              float* w = v + g8 * 8;
+              float gmax = gm[g8];
+              while (gmax > thr) {
+                int idx = 7;
+#pragma unroll
+                for (int j = 6; j >= 0; --j) idx = (w[j] == gmax) ? j : idx;       // lowest column among equals first
+                mylist[cnt] = make_key(-gmax, base_idx + uint32_t(chunk * 32 + g8 * 8 + idx));
                 ++cnt;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = (j == idx) ? -INFINITY : w[j];
+                gmax = fmax3(fmax3(w[0], w[1], w[2]), fmax3(w[3], w[4], w[5]), fmaxf(w[6], w[7]));
               }
             }
           }
           const uint32_t full = __ballot_sync(0xffffffffu, cnt > a.cap - 32);
           if (full) {
-            if (a.cap == 256) warp_compact<8>(warp_lists, a.cap, a.kp, cnt, thr, full, lane, nullptr, 0, 32, thr_g_warp);
-            else warp_compact<16>(warp_lists, a.cap, a.kp, cnt, thr, full, lane, nullptr, 0, 32, thr_g_warp);
+            const long long tc0 = dbg_me ? clock64() : 0ll;
+            const ListState ls = a.cap == 256
+                ? warp_compact<8>(warp_lists, a.cap, a.kp, cnt, thr, full, lane, nullptr, 0, 32, thr_g_warp)
+                : warp_compact<16>(warp_lists, a.cap, a.kp, cnt, thr, full, lane, nullptr, 0, 32, thr_g_warp);
+            cnt = ls.cnt;
+            thr = ls.thr;
+            if (dbg_me) { tcomp += clock64() - tc0; a.dbg[blockIdx.x * 16 + 12] += __popc(full); }
           }
+        };
+        {
+          const uint32_t tbase = tmem_base + tmem_lane + uint32_t(buf * BN);
+          uint32_t rA[32], rB[32];
+          tc_ld32(tbase, rA);
+#pragma unroll 1
+          for (int chunk = 0; chunk < BN / 32; chunk += 2) {
+            tc_wait_ld();
+            tc_ld32(tbase + uint32_t(chunk * 32 + 32), rB);
+            process(rA, chunk);
+            tc_wait_ld();
+            if (chunk + 2 < BN / 32) tc_ld32(tbase + uint32_t(chunk * 32 + 64), rA);
+            process(rB, chunk + 1);
+          }
+        }
+        if (dbg_me) {
+          a.dbg[blockIdx.x * 16 + 8] += (unsigned long long)(clock64() - t0 - tcomp);
+          a.dbg[blockIdx.x * 16 + 9] += (unsigned long long)tcomp;
+          a.dbg[blockIdx.x * 16 + 13] += 1;
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(T_EMPTY(buf));
       }
       // end of unit: emit the best kp keys of every valid query row of this warp
+      const long long te0 = (a.dbg && ewarp == 0 && lane == 0) ? clock64() : 0ll;
       const int q0 = qt * BM + ewarp * 32;
       const int valid = min(32, a.nq - q0);
       if (valid > 0) {
@@ -388,6 +446,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (a.cap == 256) warp_compact<8>(warp_lists, a.cap, a.kp, cnt, thr, 0xffffffffu, lane, out, int64_t(a.P) * a.kp, valid, thr_g_warp);
         else warp_compact<16>(warp_lists, a.cap, a.kp, cnt, thr, 0xffffffffu, lane, out, int64_t(a.P) * a.kp, valid, thr_g_warp);
       }
+      if (a.dbg && ewarp == 0 && lane == 0) a.dbg[blockIdx.x * 16 + 10] += (unsigned long long)(clock64() - te0);
     }
   }
 
@@ -651,6 +710,13 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
   a.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
   a.partial = reinterpret_cast<uint64_t*>(ws + pl.off_partial);
   a.thr_g = reinterpret_cast<uint32_t*>(ws + pl.off_thr);
+  static const bool dbg_on = getenv("B200IR_GEMM_DEBUG") != nullptr;
+  static unsigned long long* dbg_buf = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, size_t(kNumSMs) * 16 * 8);
+    cudaMemsetAsync(dbg_buf, 0, size_t(kNumSMs) * 16 * 8, st);
+    a.dbg = dbg_buf;
+  }
   {
     ProfileScope ps(PT_GEMM, st);
     cudaError_t e;
@@ -667,6 +733,21 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
     if (e != cudaSuccess) return int(e);
     e = cudaGetLastError();
     if (e != cudaSuccess) return int(e);
+  }
+  if (dbg_on) {
+    static unsigned long long host[kNumSMs * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
+    static const char* names[16] = {"prod_wait_Bempty", "prod_wait_Aempty", "prod_wait_Tempty", "mma_wait_Bfull", "mma_wait_Tempty",
+                                    "mma_wait_Afull", "-", "epi_wait_full", "epi_elements", "epi_compact", "epi_unit_end", "-",
+                                    "epi_compactions(w0)", "epi_tiles", "-", "-"};
+    fprintf(stderr, "[b200ir gemm debug] grid=%d P=%d tiles/part=%d kp=%d cap=%d (mean cycles per CTA)\n", pl.grid, pl.P, pl.tiles_per_part, pl.kp, pl.cap);
+    for (int sidx = 0; sidx < 16; ++sidx) {
+      if (names[sidx][0] == '-') continue;
+      double sum = 0, mx = 0;
+      for (int c = 0; c < pl.grid; ++c) { sum += double(host[c * 16 + sidx]); if (double(host[c * 16 + sidx]) > mx) mx = double(host[c * 16 + sidx]); }
+      fprintf(stderr, "  %-22s mean %14.0f  max %14.0f\n", names[sidx], sum / pl.grid, mx);
+    }
   }
   {
     const int rerank = (flags & B200IR_FLAG_NO_RERANK) ? 0 : 1;
