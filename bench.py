@@ -245,6 +245,8 @@ def run_headline(args):
     X = make_unit_rows(torch, ROWS_PER_GPU, DIM, 2001 + rank, dev, torch.bfloat16)
     Q = make_unit_rows(torch, NQ, DIM, 2002, dev, torch.bfloat16)
     Q_host = Q.cpu().pin_memory()
+    out_s_host = torch.empty((NQ, TOPK), dtype=torch.float32).pin_memory()
+    out_i_host = torch.empty((NQ, TOPK), dtype=torch.int64).pin_memory()
     index = ShardedIndex(X, rank * ROWS_PER_GPU)
     flags = ops.FLAG_NO_TENSOR if args.no_tensor else 0
 
@@ -252,9 +254,13 @@ def run_headline(args):
         return index.topk(Q, "cosine_similarity", TOPK, flags=flags)
 
     def step_e2e():
+        # the call a user makes, host buffers on both sides: pinned queries -> device, search, results -> pinned host
         q = Q_host.to(dev, non_blocking=True)
         s, i = index.topk(q, "cosine_similarity", TOPK, flags=flags)
-        return s.cpu(), i.cpu()
+        out_s_host.copy_(s, non_blocking=True)
+        out_i_host.copy_(i, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # results are usable on the host after every step
+        return out_s_host, out_i_host
 
     def barrier():
         torch.cuda.synchronize()
