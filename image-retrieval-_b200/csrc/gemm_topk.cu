@@ -4,11 +4,11 @@
 // Replaces the scan loops of app_pipeline.py:156-172 / :296-328 for bf16 stores: the query batch
 // and the database are the A and B operands (both K-major) of C = Q . X^T.
 //
-//   grid      : one persistent CTA per SM, 256 threads, warp-specialised:
+//   grid      : one persistent CTA per SM, 384 threads, warp-specialised:
 //                 warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor, 128B-swizzled tiles)
 //                 warp 1 lane 0 : MMA issuer    (tcgen05.mma.cta_group::1.kind::f16, M128 N256 K16)
 //                 warp 2        : TMEM allocator (512 columns = two 128x256 fp32 accumulators)
-//                 warps 4..7    : epilogue, one thread per query row (TMEM lane)
+//                 warps 4..11   : epilogue, two warps per TMEM lane quarter sharing one candidate list per query
 //   work unit : (128-query tile, contiguous range of 256-row database tiles).  The query tile stays
 //               resident in shared memory (A, up to 128 KB for D = 512) for the whole unit; database
 //               tiles stream through a 3-stage 32 KB ring (B).
@@ -43,8 +43,9 @@ constexpr int SMEM_A = MAX_KB * A_KB_BYTES;  // 128 KB
 constexpr int SMEM_B = B_STAGES * B_STAGE_BYTES;   // 96 KB
 constexpr int SMEM_SCALE = 2 * BN * 4;       // double-buffered per-column scale (rnorm / sqnorm)
 constexpr int SMEM_BARS = 128;
-constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS;   // 231,552 B <= 232,448
-constexpr int THREADS = 256;
+constexpr int SMEM_CNT = BM * 4;            // per-query candidate counters shared by the two epilogue warps of a quarter
+constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS + SMEM_CNT;   // 232,064 B <= 232,448
+constexpr int THREADS = 384;           // 4 control warps + 8 epilogue warps (two per TMEM lane quarter)
 constexpr int TMEM_COLS = 512;
 
 enum Mode { MODE_COS = 0, MODE_ABSCOS = 1, MODE_L2 = 2 };
@@ -152,16 +153,17 @@ __device__ __forceinline__ void import_threshold(const uint32_t* thr_g_q, float&
   }
 }
 
-struct ListState { int cnt; float thr; };     // returned by value: both stay in registers in the caller
-
+// Warp-cooperative compaction of the candidate lists of the query rows in `mask` (bit L = row L of this TMEM lane
+// quarter): sort, keep the best kp, publish the k'-th rank value.  Counters live in shared memory (`cnt_q`, one
+// per row of the quarter) because two epilogue warps append to the same list.  If `out` is set the sorted list
+// goes to the unit's output slot instead of back to the scratch list.
 template <int E>
-__device__ __noinline__ ListState warp_compact(uint64_t* warp_lists, int cap, int kp, int cnt, float thr, uint32_t mask,
-                                               int lane, uint64_t* out, int64_t out_stride, int valid_lanes, uint32_t* thr_g_warp) {
-  __syncwarp();
+__device__ __noinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp, int* cnt_q, uint32_t mask, int lane,
+                                          uint64_t* out, int64_t out_stride, int valid_lanes, uint32_t* thr_g_warp) {
   while (mask) {
     const int L = __ffs(mask) - 1;
     mask &= mask - 1;
-    const int n = __shfl_sync(0xffffffffu, cnt, L);
+    const int n = cnt_q[L];
     uint64_t* list = warp_lists + size_t(L) * cap;
     uint64_t r[E];
 #pragma unroll
@@ -181,13 +183,9 @@ __device__ __noinline__ ListState warp_compact(uint64_t* warp_lists, int cap, in
 #pragma unroll
       for (int e = 0; e < E; ++e) if (e == src_e) kth = r[e];
       kth = shfl_u64(kth, src_lane);
-      if (lane == L) {
-        cnt = n < kp ? n : kp;
-        if (n >= kp) {
-          thr = fmaxf(thr, -key_rank(kth));     // keys hold r = -v: accept only v > thr from now on
-          atomicMin(thr_g_warp + L, uint32_t(kth >> 32));
-          import_threshold(thr_g_warp + L, thr);
-        }
+      if (lane == 0) {
+        cnt_q[L] = n < kp ? n : kp;
+        if (n >= kp) atomicMin(thr_g_warp + L, uint32_t(kth >> 32));
       }
     } else if (L < valid_lanes) {
       uint64_t* dst = out + int64_t(L) * out_stride;
@@ -197,9 +195,22 @@ __device__ __noinline__ ListState warp_compact(uint64_t* warp_lists, int cap, in
         if (i < kp) dst[i] = r[e];
       }
     }
+    __syncwarp();
   }
-  __syncwarp();
-  return ListState{cnt, thr};
+}
+
+// every other set bit of `m`, starting with set bit number `which` (0 or 1): splits compaction work between the
+// two epilogue warps of a quarter
+__device__ __forceinline__ uint32_t alternate_bits(uint32_t m, int which) {
+  uint32_t out = 0;
+  int k = 0;
+  while (m) {
+    const uint32_t low = m & (0u - m);
+    if ((k & 1) == which) out |= low;
+    m ^= low;
+    ++k;
+  }
+  return out;
 }
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -225,6 +236,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   float* sScale = reinterpret_cast<float*>(smem + SMEM_A + SMEM_B);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_A + SMEM_B + SMEM_SCALE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  int* cnt_s = reinterpret_cast<int*>(smem + SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS);
 
   const uint32_t bar0 = smem_u32(bars);
   auto B_FULL = [&](int s) { return bar0 + 8u * s; };
@@ -247,7 +259,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < B_STAGES; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
     mbar_init(A_FULL, 1);
     mbar_init(A_EMPTY, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(T_FULL(b), 1); mbar_init(T_EMPTY(b), 4); mbar_init(S_FULL(b), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(T_FULL(b), 1); mbar_init(T_EMPTY(b), 8); mbar_init(S_FULL(b), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -336,26 +348,37 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: one thread per query row =====================
-    const int ewarp = warp - 4;
-    const int row = ewarp * 32 + lane;
-    uint64_t* warp_lists = a.cand + (size_t(blockIdx.x) * BM + ewarp * 32) * a.cap;
+    // ===================== epilogue =====================
+    // Two warps per TMEM lane quarter (warp % 4 selects the lanes a warp may read): warp `half` takes the chunks
+    // 2i + half of every tile, so each scheduler always has a second epilogue warp to issue from while the other
+    // waits on a dependency, a branch or a TMEM load.  The two threads that serve one query row share ONE candidate
+    // list (slots handed out by a shared-memory atomic counter) and meet at a 64-thread named barrier after every
+    // chunk pair, where a full list is compacted (the lists to compact are split between the two warps).
+    const int quarter = (warp - 4) & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = quarter * 32 + lane;
+    const int pair_bar = 1 + quarter;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
+    uint64_t* warp_lists = a.cand + (size_t(blockIdx.x) * BM + quarter * 32) * a.cap;
     uint64_t* mylist = warp_lists + size_t(lane) * a.cap;
-    const uint32_t tmem_lane = uint32_t(ewarp * 32) << 16;
+    int* cnt_q = cnt_s + quarter * 32;
+    int* mycnt = cnt_q + lane;
+    const uint32_t tmem_lane = uint32_t(quarter * 32) << 16;
+    const bool dbg_me = a.dbg && warp == 4 && lane == 0;
     uint32_t titer = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int qt = unit % a.num_qtiles, p = unit / a.num_qtiles;
       const int q = qt * BM + row;
       float thr = q < a.nq ? -INFINITY : INFINITY;             // padding rows of the last query tile accept nothing
-      int cnt = 0;
+      if (half == 0) *mycnt = 0;
+      pair_sync();
       const int tile0 = p * a.tiles_per_part;
       const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
-      uint32_t* thr_g_warp = a.thr_g + qt * BM + ewarp * 32;
+      uint32_t* thr_g_warp = a.thr_g + qt * BM + quarter * 32;
       import_threshold(thr_g_warp + lane, thr);
       for (int t = tile0; t < tile1; ++t, ++titer) {
         const int buf = titer & 1;
         if (((t - tile0) & 15) == 15) import_threshold(thr_g_warp + lane, thr);
-        const bool dbg_me = a.dbg && ewarp == 0 && lane == 0;
         long long t0 = dbg_me ? clock64() : 0ll;
         mbar_wait(S_FULL(buf), (titer >> 1) & 1);
         mbar_wait(T_FULL(buf), (titer >> 1) & 1);
@@ -364,9 +387,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const float* sc = sScale + buf * BN;
         const uint32_t base_idx = uint32_t(t) * BN;
-        // 8 chunks of 32 columns, software-pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is
-        // scored (register double buffer rA / rB).
-        auto process = [&](uint32_t (&r)[32], int chunk) {
+        const uint32_t tbase = tmem_base + tmem_lane + uint32_t(buf * BN);
+#pragma unroll 1
+        for (int pair = 0; pair < BN / 64; ++pair) {
+          const int chunk = pair * 2 + half;
+          uint32_t r[32];
+          tc_ld32(tbase + uint32_t(chunk * 32), r);
+          tc_wait_ld();
           // branch-free pre-filter: score all 32 columns and reduce with 3-input max (max.f32 skips NaN = masked
           // columns).  Only a thread whose 8-column group maximum beats its threshold touches that group, and it
           // extracts the hits by arg-max (select chains, no per-element branches).
@@ -395,58 +422,52 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 int idx = 7;
 #pragma unroll
                 for (int j = 6; j >= 0; --j) idx = (w[j] == gmax) ? j : idx;       // lowest column among equals first
-                mylist[cnt] = make_key(-gmax, base_idx + uint32_t(chunk * 32 + g8 * 8 + idx));
-                ++cnt;
+                const int slot = atomicAdd(mycnt, 1);
+                mylist[slot] = make_key(-gmax, base_idx + uint32_t(chunk * 32 + g8 * 8 + idx));
 #pragma unroll
                 for (int j = 0; j < 8; ++j) w[j] = (j == idx) ? -INFINITY : w[j];
                 gmax = fmax3(fmax3(w[0], w[1], w[2]), fmax3(w[3], w[4], w[5]), fmaxf(w[6], w[7]));
               }
             }
           }
-          const uint32_t full = __ballot_sync(0xffffffffu, cnt > a.cap - 32);
+          // both warps of the quarter finished this chunk pair: at most 64 new entries per list
+          pair_sync();
+          const uint32_t full = __ballot_sync(0xffffffffu, *reinterpret_cast<volatile int*>(mycnt) > a.cap - 64);
           if (full) {
             const long long tc0 = dbg_me ? clock64() : 0ll;
-            const ListState ls = a.cap == 256
-                ? warp_compact<8>(warp_lists, a.cap, a.kp, cnt, thr, full, lane, nullptr, 0, 32, thr_g_warp)
-                : warp_compact<16>(warp_lists, a.cap, a.kp, cnt, thr, full, lane, nullptr, 0, 32, thr_g_warp);
-            cnt = ls.cnt;
-            thr = ls.thr;
+            const uint32_t mine = alternate_bits(full, half);
+            if (a.cap == 256) warp_compact<8>(warp_lists, a.cap, a.kp, cnt_q, mine, lane, nullptr, 0, 32, thr_g_warp);
+            else warp_compact<16>(warp_lists, a.cap, a.kp, cnt_q, mine, lane, nullptr, 0, 32, thr_g_warp);
+            pair_sync();
+            if ((full >> lane) & 1) {
+              if (*reinterpret_cast<volatile int*>(mycnt) >= a.kp)
+                thr = fmaxf(thr, -key_rank(*reinterpret_cast<volatile uint64_t*>(mylist + a.kp - 1)));   // accept only v > thr
+              import_threshold(thr_g_warp + lane, thr);
+            }
             if (dbg_me) { tcomp += clock64() - tc0; a.dbg[blockIdx.x * 16 + 12] += __popc(full); }
           }
-        };
-        {
-          const uint32_t tbase = tmem_base + tmem_lane + uint32_t(buf * BN);
-          uint32_t rA[32], rB[32];
-          tc_ld32(tbase, rA);
-#pragma unroll 1
-          for (int chunk = 0; chunk < BN / 32; chunk += 2) {
-            tc_wait_ld();
-            tc_ld32(tbase + uint32_t(chunk * 32 + 32), rB);
-            process(rA, chunk);
-            tc_wait_ld();
-            if (chunk + 2 < BN / 32) tc_ld32(tbase + uint32_t(chunk * 32 + 64), rA);
-            process(rB, chunk + 1);
-          }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(T_EMPTY(buf));
         if (dbg_me) {
           a.dbg[blockIdx.x * 16 + 8] += (unsigned long long)(clock64() - t0 - tcomp);
           a.dbg[blockIdx.x * 16 + 9] += (unsigned long long)tcomp;
           a.dbg[blockIdx.x * 16 + 13] += 1;
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(T_EMPTY(buf));
       }
-      // end of unit: emit the best kp keys of every valid query row of this warp
-      const long long te0 = (a.dbg && ewarp == 0 && lane == 0) ? clock64() : 0ll;
-      const int q0 = qt * BM + ewarp * 32;
+      // end of unit: emit the best kp keys of every valid query row of this quarter (rows split between the warps)
+      const long long te0 = dbg_me ? clock64() : 0ll;
+      const int q0 = qt * BM + quarter * 32;
       const int valid = min(32, a.nq - q0);
       if (valid > 0) {
         uint64_t* out = a.partial + (int64_t(q0) * a.P + p) * a.kp;
-        if (a.cap == 256) warp_compact<8>(warp_lists, a.cap, a.kp, cnt, thr, 0xffffffffu, lane, out, int64_t(a.P) * a.kp, valid, thr_g_warp);
-        else warp_compact<16>(warp_lists, a.cap, a.kp, cnt, thr, 0xffffffffu, lane, out, int64_t(a.P) * a.kp, valid, thr_g_warp);
+        const uint32_t mine = half ? 0xffff0000u : 0x0000ffffu;
+        if (a.cap == 256) warp_compact<8>(warp_lists, a.cap, a.kp, cnt_q, mine, lane, out, int64_t(a.P) * a.kp, valid, thr_g_warp);
+        else warp_compact<16>(warp_lists, a.cap, a.kp, cnt_q, mine, lane, out, int64_t(a.P) * a.kp, valid, thr_g_warp);
       }
-      if (a.dbg && ewarp == 0 && lane == 0) a.dbg[blockIdx.x * 16 + 10] += (unsigned long long)(clock64() - te0);
+      pair_sync();                                             // lists and counters may be reused by the next unit
+      if (dbg_me) a.dbg[blockIdx.x * 16 + 10] += (unsigned long long)(clock64() - te0);
     }
   }
 
