@@ -319,8 +319,16 @@ def run_headline(args):
     if dom:
         peak = pk.get("bf16_tflops_sustained", PEAKS_FALLBACK["bf16_tflops_sustained"])
         ach = flops / (kern[dom] * 1e-3) / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tr = json.load(f).get(dom)
+            if tr:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]      # measured under ncu, per launch
+        except Exception:  # noqa: BLE001
+            pass
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": None, "kernel_ms": kern[dom], "kernels_ms": kern,
+                    "traffic": traffic, "kernel_ms": kern[dom], "kernels_ms": kern,
                     "algorithmic_flops_per_launch": flops, "peak_source": pk["_source"] + ", sustained bf16 (kernel timed inside back-to-back steps)"}
 
     # parity spot-check of the timed result against the oracle (bounded: 8 queries, fp64 truth)
