@@ -503,32 +503,48 @@ __global__ void row_scale_kernel(const __nv_bfloat16* __restrict__ X, int64_t N,
 // arithmetic (direct dot / direct sum of squared differences, fp32, no cancellation), write the k winners.
 template <int E>
 __global__ void __launch_bounds__(128)
-gemm_finalize_kernel(const uint64_t* __restrict__ partial, const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ X,
-                     int nq, int D, int P, int kp, int k, int mode, int rerank, MetricParams mp, int64_t index_offset,
+gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __restrict__ thr_g, const __nv_bfloat16* __restrict__ Q,
+                     const __nv_bfloat16* __restrict__ X, int nq, int D, int P, int kp, int k, int mode, int rerank, MetricParams mp,
+                     int64_t index_offset,
                      float* __restrict__ out_score, int64_t* __restrict__ out_idx) {
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (q >= nq) return;
   const int64_t per_query = int64_t(P) * kp;
   const uint64_t* src = partial + int64_t(q) * per_query;
+  // Keys worse than the final published threshold of this query (the k'-th best of some partition) cannot be
+  // among the global k' best: drop them while streaming the P lists through the sorter.  Survivors are compacted
+  // with ballot prefix sums, so usually one or two sort rounds are enough instead of P * kp / (32 E - kp).
+  const uint64_t limit = (uint64_t(thr_g[q]) << 32) | 0xffffffffull;       // 0xffffffff.. = none published: keep all
+  __shared__ uint64_t stage_s[4][32 * E];
+  uint64_t* stage = stage_s[threadIdx.x >> 5];
   uint64_t r[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) r[e] = kKeyInf;
-  int kept = 0;
-  int64_t pos = 0;
-  do {
+  int kept = 0;            // sorted survivors of earlier rounds occupy register positions [0, kept)
+  int fill = 0;            // survivors staged in shared memory for the next round
+  for (int64_t base = 0; base < per_query; base += 32) {
+    const int64_t sidx = base + lane;
+    const uint64_t key = sidx < per_query ? src[sidx] : kKeyInf;
+    const bool keep = key <= limit && key != kKeyInf;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (keep) stage[fill + __popc(m & ((1u << lane) - 1))] = key;
+    fill += __popc(m);
+    if (fill > 32 * E - kept - 32 || base + 32 >= per_query) {
+      __syncwarp();
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int i = lane * E + e;
-      if (i >= kept) {
-        const int64_t s = pos + (i - kept);
-        r[e] = s < per_query ? src[s] : kKeyInf;
+      for (int e = 0; e < E; ++e) {
+        const int i = lane * E + e;
+        if (i >= kept) r[e] = (i - kept) < fill ? stage[i - kept] : kKeyInf;
       }
+      warp_sort<E>(r, lane);
+      kept = min(kept + fill, kp);
+      fill = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) if (lane * E + e >= kept) r[e] = kKeyInf;
+      __syncwarp();
     }
-    pos += 32 * E - kept;
-    warp_sort<E>(r, lane);
-    kept = kp;
-  } while (pos < per_query);
+  }
 
   // query row in registers: lane holds elements [8*(lane + 32 j), +8), j = 0, 1 (D <= 512)
   const __nv_bfloat16* qrow = Q + int64_t(q) * D;
@@ -777,9 +793,9 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
     const __nv_bfloat16* Qb = static_cast<const __nv_bfloat16*>(Q);
     const __nv_bfloat16* Xb = static_cast<const __nv_bfloat16*>(X);
     if (pl.cap == 256)
-      gemm_finalize_kernel<8><<<blocks, 128, 0, st>>>(a.partial, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, out_score, out_idx);
+      gemm_finalize_kernel<8><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, out_score, out_idx);
     else
-      gemm_finalize_kernel<16><<<blocks, 128, 0, st>>>(a.partial, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, out_score, out_idx);
+      gemm_finalize_kernel<16><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, out_score, out_idx);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return int(e);
   }

@@ -335,3 +335,71 @@ def test_tensor_path_sharded_and_abs(ops):
     s, i = ops.topk(Qt, Xt, "cosine_similarity", 20, abs_score=True)
     truth = np.abs(OM.pairwise_f64(Q, X, "cosine_similarity"))
     check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 20, True, rtol=1e-5, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------- BASELINE full sizes
+def _device_unit_rows(n, d, seed, dtype):
+    import torch
+    out = torch.empty((n, d), dtype=dtype, device="cuda")
+    for c, s in enumerate(range(0, n, 250_000)):
+        g = torch.Generator(device="cuda")
+        g.manual_seed(seed * 1000 + c)
+        e = min(n, s + 250_000)
+        x = torch.randn((e - s, d), generator=g, device="cuda", dtype=torch.float32)
+        x /= x.norm(dim=1, keepdim=True)
+        out[s:e] = x.to(dtype)
+    return out
+
+
+def test_full_size_config2_cosine_top100(ops):
+    """BASELINE configs[1] at full size (1M x 512 bf16, 10k queries, top-100): a sample of queries against the
+    fp64 oracle, plus size-independent properties: sharded == unsharded, angle/cosine-distance consistent."""
+    import torch
+    X = _device_unit_rows(1_000_000, 512, 2001, torch.bfloat16)
+    Q = _device_unit_rows(10_000, 512, 2002, torch.bfloat16)
+    s, i = ops.topk(Q, X, "cosine_similarity", 100)
+    sel = [0, 1, 4999, 9999]
+    Xh = X.float().cpu().numpy()
+    truth = OM.pairwise_f64(Q[sel].float().cpu().numpy(), Xh, "cosine_similarity")
+    disputed = check_topk(s[sel].cpu().numpy(), i[sel].cpu().numpy(), truth, 100, True, rtol=1e-5, atol=2e-6)
+    assert disputed <= 2
+    # sortedness + uniqueness over the whole result
+    assert bool((s[:, 1:] <= s[:, :-1]).all())
+    srt = torch.sort(i, dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())
+    # row-sharded (4 shards) + merge == unsharded, exactly
+    ps, pi = [], []
+    for r in range(4):
+        b, e = r * 250_000, (r + 1) * 250_000
+        ss, ii = ops.topk(Q[:512], X[b:e], "cosine_similarity", 100, index_offset=b)
+        ps.append(ss); pi.append(ii)
+    ms, mi = ops.topk_merge(torch.stack(ps), torch.stack(pi), True)
+    assert torch.equal(mi, i[:512]) and torch.equal(ms, s[:512])
+    # angle selects the same rows (its own order re-sorts fp32-equal angles by index, so compare as sets)
+    sa, ia = ops.topk(Q[:256], X, "angular_distance", 100)
+    assert torch.equal(torch.sort(ia, dim=1).values, torch.sort(i[:256], dim=1).values)
+    torch.testing.assert_close(torch.cos(sa), s[:256], rtol=1e-5, atol=2e-6)
+    assert bool((sa[:, 1:] >= sa[:, :-1]).all())
+
+
+def test_full_size_config3_l1_linf_top10(ops):
+    """BASELINE configs[2] at full size (1M x 2048 fp32): L1 / Linf top-10 of an 8-query batch vs the fp64 oracle."""
+    import torch
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3001)
+    X = torch.relu(torch.randn((1_000_000, 2048), generator=g, device="cuda"))
+    Q = torch.relu(torch.randn((8, 2048), generator=g, device="cuda"))
+    Xh = X.cpu().numpy()
+    Qh = Q.cpu().numpy()
+    for metric in ("l1", "linf"):
+        s, i = ops.topk(Q, X, metric, 10)
+        truth = np.stack([OM.pairwise_f64(Qh[j:j + 1], Xh, metric, chunk=50_000)[0] for j in range(2)])
+        check_topk(s[:2].cpu().numpy(), i[:2].cpu().numpy(), truth, 10, False, rtol=1e-5, atol=1e-30)
+        # every returned score equals the reference formula on the returned row (all 8 queries)
+        rows = Xh[i.cpu().numpy()]                                       # (8, 10, 2048)
+        d = np.abs(rows.astype(np.float64) - Qh[:, None, :].astype(np.float64))
+        want = d.sum(-1) / 2048 if metric == "l1" else d.max(-1)
+        np.testing.assert_allclose(s.cpu().numpy(), want, rtol=1e-5)
+        # a second identical call is bit-identical (no atomics-order dependence in the result)
+        s2, i2 = ops.topk(Q, X, metric, 10)
+        assert torch.equal(i2, i) and torch.equal(s2, s)
