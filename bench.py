@@ -459,6 +459,67 @@ def run_side(args):
     return 0
 
 
+def run_config4(args):
+    """BASELINE configs[3]: 10M x 512 database row-sharded over the ranks (strong scaling: total rows fixed), all five
+    metrics, one all-gather + merge per search.  bf16 rows for the tensor-core metrics (10k queries, k=100), fp32 rows
+    for L1 / Linf (8 queries, k=10).  Prints one JSON line with per-metric queries/s (max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from image_retrieval_b200 import ops
+    from image_retrieval_b200.sharded import ShardedIndex, shard_range
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    total = args.rows or 10_000_000
+    b, e = shard_range(total, world, rank)
+    n_local = e - b
+    res = {}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    Xb = make_unit_rows(torch, n_local, DIM, 4001 + rank, dev, torch.bfloat16)
+    Qb = make_unit_rows(torch, NQ, DIM, 4002, dev, torch.bfloat16)
+    idx = ShardedIndex(Xb, b)
+    for metric in ("cosine_similarity", "angular_distance", "l2"):
+        ms = timed(lambda: idx.topk(Qb, metric, TOPK))
+        res[metric] = {"queries": NQ, "k": TOPK, "dtype": "bf16", "ms": ms, "queries_per_s": NQ / (ms * 1e-3)}
+    del Xb, idx
+    torch.cuda.empty_cache()
+    Xf = make_unit_rows(torch, n_local, DIM, 4001 + rank, dev, torch.float32)
+    Qf = make_unit_rows(torch, 8, DIM, 4003, dev, torch.float32)
+    idx = ShardedIndex(Xf, b)
+    for metric in ("l1", "linf"):
+        ms = timed(lambda: idx.topk(Qf, metric, 10))
+        res[metric] = {"queries": 8, "k": 10, "dtype": "f32", "ms": ms, "queries_per_s": 8 / (ms * 1e-3),
+                       "hbm_GBps_per_gpu": n_local * DIM * 4 / (ms * 1e-3) / 1e9}
+    if rank == 0:
+        print(json.dumps({"metric": "queries/sec per metric (config 4: 10M x 512 row-sharded, all-gather top-k merge)",
+                          "n_gpus": world, "steps": args.steps, "db_rows_total": total, "rows_per_gpu": n_local,
+                          "scaling": "strong", "results": res}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -476,6 +537,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "config4":
+        return run_config4(args)
     if args.workload != "headline":
         return run_side(args)
     return run_headline(args)
