@@ -238,6 +238,8 @@ def run_headline(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (no NCCL version banner)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     ops.device()

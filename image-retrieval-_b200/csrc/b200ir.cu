@@ -219,7 +219,18 @@ int b200ir_topk_merge(int descending, const float* score, const int64_t* idx, in
   if (k < 1 || k > B200IR_MAX_K) return B200IR_E_K;
   if (nq == 0) return 0;
   if (!score || !idx || !out_score || !out_idx) return B200IR_E_ARG;
-  return int(launch_merge(descending ? 1 : 0, score, idx, R, nq, k, out_score, out_idx, static_cast<cudaStream_t>(stream)));
+  return int(launch_merge(descending ? 1 : 0, score, idx, nq * k, nq * k, R, nq, k, out_score, out_idx, static_cast<cudaStream_t>(stream)));
+}
+
+int b200ir_topk_merge_strided(int descending, const float* score, const int64_t* idx, int64_t score_shard_stride,
+                              int64_t idx_shard_stride, int R, int64_t nq, int k, float* out_score, int64_t* out_idx,
+                              void* stream) {
+  if (R < 1 || nq < 0 || score_shard_stride < 0 || idx_shard_stride < 0) return B200IR_E_ARG;
+  if (k < 1 || k > B200IR_MAX_K) return B200IR_E_K;
+  if (nq == 0) return 0;
+  if (!score || !idx || !out_score || !out_idx) return B200IR_E_ARG;
+  return int(launch_merge(descending ? 1 : 0, score, idx, score_shard_stride, idx_shard_stride, R, nq, k, out_score, out_idx,
+                          static_cast<cudaStream_t>(stream)));
 }
 
 int b200ir_histogram(int colorspace, const uint8_t* img, int64_t B, int H, int W, int bins_per_channel,

@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(128) finalize_topk_kernel(const uint64_t* __re
 // Cross-shard merge: score/idx [R, nq, k] -> [nq, k] ordered by (score, global idx).
 template <int E>
 __global__ void __launch_bounds__(128) merge_topk_kernel(int descending, const float* __restrict__ score,
-                                                        const int64_t* __restrict__ idx, int R, int nq, int k,
+                                                        const int64_t* __restrict__ idx, int64_t score_stride,
+                                                        int64_t idx_stride, int R, int nq, int k,
                                                         float* __restrict__ out_score, int64_t* __restrict__ out_idx) {
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -98,10 +99,10 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(int descending, const f
         key128_t key = kInf;
         if (s < per_query) {
           const int shard = int(s / k), j = int(s % k);
-          const int64_t off = (int64_t(shard) * nq + q) * k + j;
-          const int64_t id = idx[off];
+          const int64_t off = int64_t(q) * k + j;
+          const int64_t id = idx[int64_t(shard) * idx_stride + off];
           if (id >= 0) {
-            const float v = score[off];
+            const float v = score[int64_t(shard) * score_stride + off];
             key = (key128_t(f32_to_ordered(descending ? -v : v)) << 64) | key128_t(uint64_t(id));
           }
         }
@@ -140,12 +141,12 @@ inline cudaError_t launch_finalize(const uint64_t* partial, int64_t nq, int64_t 
   return cudaGetLastError();
 }
 
-inline cudaError_t launch_merge(int descending, const float* score, const int64_t* idx, int R, int64_t nq, int k,
-                                float* out_score, int64_t* out_idx, cudaStream_t st) {
+inline cudaError_t launch_merge(int descending, const float* score, const int64_t* idx, int64_t score_stride, int64_t idx_stride,
+                                int R, int64_t nq, int k, float* out_score, int64_t* out_idx, cudaStream_t st) {
   const int blocks = int(ceil_div64(nq, 4));
   ProfileScope ps(PT_MERGE, st);
-  if (k <= 128) merge_topk_kernel<8><<<blocks, 128, 0, st>>>(descending, score, idx, R, int(nq), k, out_score, out_idx);
-  else merge_topk_kernel<16><<<blocks, 128, 0, st>>>(descending, score, idx, R, int(nq), k, out_score, out_idx);
+  if (k <= 128) merge_topk_kernel<8><<<blocks, 128, 0, st>>>(descending, score, idx, score_stride, idx_stride, R, int(nq), k, out_score, out_idx);
+  else merge_topk_kernel<16><<<blocks, 128, 0, st>>>(descending, score, idx, score_stride, idx_stride, R, int(nq), k, out_score, out_idx);
   return cudaGetLastError();
 }
 

@@ -121,7 +121,7 @@ def row_sqnorms(X):
     return out
 
 
-def topk(Q, X, metric, k, *, index_offset=0, normalized=True, abs_score=False, params=None, flags=0):
+def topk(Q, X, metric, k, *, index_offset=0, normalized=True, abs_score=False, params=None, flags=0, out=None):
     """Fused distance + top-k.  Returns (scores (nq,k) fp32, indices (nq,k) int64) on the device,
     best first, ties by ascending index; slots past N hold (+-inf, -1)."""
     m = metric_id(metric)
@@ -135,8 +135,14 @@ def topk(Q, X, metric, k, *, index_offset=0, normalized=True, abs_score=False, p
     nq, D = Q.shape
     N = X.shape[0]
     f = _flags(normalized, abs_score, flags)
-    scores = torch.empty((nq, k), dtype=torch.float32, device=X.device)
-    idx = torch.empty((nq, k), dtype=torch.int64, device=X.device)
+    if out is None:
+        scores = torch.empty((nq, k), dtype=torch.float32, device=X.device)
+        idx = torch.empty((nq, k), dtype=torch.int64, device=X.device)
+    else:
+        scores, idx = out
+        if scores.shape != (nq, k) or idx.shape != (nq, k) or scores.dtype != torch.float32 or idx.dtype != torch.int64 \
+                or not scores.is_contiguous() or not idx.is_contiguous():
+            raise ValueError("out=(scores, idx) must be contiguous (nq, k) fp32 / int64 tensors")
     need = lib.b200ir_topk_workspace_bytes(m, _dtype_id(X), nq, N, D, k, f)
     ws = _workspace(need, X.device)
     st = lib.b200ir_topk(m, _dtype_id(X), _ptr(Q), nq, _ptr(X), N, D, k, int(index_offset), f, _weights(params),
@@ -177,6 +183,22 @@ def topk_merge(scores, idx, descending):
     lib = _lib.load()
     _lib.check(lib.b200ir_topk_merge(1 if descending else 0, _ptr(scores), _ptr(idx), R, nq, k, _ptr(out_s), _ptr(out_i),
                                      _stream()), "topk_merge")
+    return out_s, out_i
+
+
+def topk_merge_packed(gathered, R, nq, k, score_bytes, descending):
+    """Merge straight out of the receive buffer of ONE packed all-gather: `gathered` is R records of
+    [nq*k fp32 scores | pad | nq*k int64 ids], `score_bytes` = offset of the ids inside a record."""
+    device()
+    rec = gathered.numel() // R
+    g = gathered.view(R, rec)
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=gathered.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=gathered.device)
+    lib = _lib.load()
+    st = lib.b200ir_topk_merge_strided(1 if descending else 0, ctypes.c_void_p(g.data_ptr()),
+                                       ctypes.c_void_p(g.data_ptr() + score_bytes), rec // 4, rec // 8, R, nq, k,
+                                       _ptr(out_s), _ptr(out_i), _stream())
+    _lib.check(st, "topk_merge_strided")
     return out_s, out_i
 
 

@@ -28,6 +28,10 @@ def _default_merge(scores, idx, descending):
     return ops.topk_merge(scores, idx, descending)
 
 
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
 class ShardedIndex:
     def __init__(self, local_rows, row_begin, group=None, local_topk=None, merge=None):
         self.X = local_rows
@@ -39,8 +43,11 @@ class ShardedIndex:
     def topk(self, Q, metric, k, **kw):
         """Global top-k over all shards; every rank returns the same (scores, indices)."""
         m = ops.metric_id(metric)
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if multi and self.local_topk is _default_local and self.merge is _default_merge:
+            return self._topk_packed(Q, metric, m, k, **kw)
         s, i = self.local_topk(Q, self.X, metric, k, self.row_begin, **kw)
-        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+        if not multi:
             return s, i
         R = dist.get_world_size(self.group)
         nq = s.shape[0]
@@ -54,3 +61,19 @@ class ShardedIndex:
         all_s = gathered[:, 0].to(torch.int32).view(torch.float32).contiguous()
         all_i = gathered[:, 1].contiguous()
         return self.merge(all_s, all_i, m in ops.DESCENDING)
+
+    def _topk_packed(self, Q, metric, m, k, **kw):
+        """CUDA fast path: the local search writes scores and ids into ONE byte record, a single all-gather moves
+        the records, and the merge kernel reads the receive buffer in place (no pack / unpack kernels)."""
+        R = dist.get_world_size(self.group)
+        Qd = ops.as_device_matrix(Q, dtype=self.X.dtype if isinstance(self.X, torch.Tensor) else None)
+        nq = Qd.shape[0]
+        score_bytes = _round_up(nq * k * 4, 16)
+        rec = _round_up(score_bytes + nq * k * 8, 16)
+        buf = torch.empty(rec, dtype=torch.uint8, device=Qd.device)
+        s = buf[:nq * k * 4].view(torch.float32).view(nq, k)
+        i = buf[score_bytes:score_bytes + nq * k * 8].view(torch.int64).view(nq, k)
+        ops.topk(Qd, self.X, metric, k, index_offset=self.row_begin, out=(s, i), **kw)
+        gathered = torch.empty(R * rec, dtype=torch.uint8, device=Qd.device)
+        dist.all_gather_into_tensor(gathered, buf, group=self.group)
+        return ops.topk_merge_packed(gathered, R, nq, k, score_bytes, m in ops.DESCENDING)

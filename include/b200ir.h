@@ -118,6 +118,11 @@ int b200ir_pairwise(int metric, int dtype, const void* Q, int64_t nq, const void
 int b200ir_topk_merge(int descending, const float* score, const int64_t* idx, int R, int64_t nq, int k,
                       float* out_score, int64_t* out_idx, void* stream);
 
+/* Same merge on lists that sit `*_shard_stride` ELEMENTS apart per shard (the receive buffer of one packed all-gather). */
+int b200ir_topk_merge_strided(int descending, const float* score, const int64_t* idx, int64_t score_shard_stride,
+                              int64_t idx_shard_stride, int R, int64_t nq, int k, float* out_score, int64_t* out_idx,
+                              void* stream);
+
 /*
  * 512-bin joint colour histogram of uint8 images, img [B, H, W, 3] interleaved RGB,
  * out_counts [B, bins^3] uint32, bin = (c0bin*bins + c1bin)*bins + c2bin with

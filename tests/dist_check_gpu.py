@@ -1,0 +1,48 @@
+"""Multi-GPU check (run under torchrun on a GPU box): the row-sharded search over NCCL equals the single-GPU search
+exactly, for a tensor-core metric and a scan metric.  Not collected by pytest (needs >= 2 GPUs):
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_check_gpu.py
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from image_retrieval_b200 import ops  # noqa: E402
+from image_retrieval_b200.sharded import ShardedIndex, shard_range  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234)
+    N, D = 200_003, 512
+    X = torch.randn((N, D), generator=g, device="cuda")
+    Q = torch.randn((300, D), generator=g, device="cuda")
+    X[150_000] = X[7]                                   # tie across shards -> lower global index first
+    b, e = shard_range(N, world, rank)
+    ok = True
+    for dtype, metric, k in ((torch.bfloat16, "cosine_similarity", 100), (torch.bfloat16, "l2", 10),
+                             (torch.float32, "l1", 10), (torch.float32, "linf", 7)):
+        Xd, Qd = X.to(dtype), Q.to(dtype)
+        s1, i1 = ops.topk(Qd, Xd, metric, k)
+        s2, i2 = ShardedIndex(Xd[b:e].contiguous(), b).topk(Qd, metric, k)
+        same = torch.equal(i1, i2) and torch.equal(s1, s2)
+        ok = ok and same
+        if rank == 0:
+            print(f"{metric:18s} {str(dtype):15s} k={k:3d} sharded==single: {same}")
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    if flag.item() != 1:
+        raise SystemExit("MISMATCH")
+    if rank == 0:
+        print("dist check ok")
+
+
+if __name__ == "__main__":
+    main()
