@@ -22,7 +22,7 @@ __device__ __forceinline__ int hsv_bin(int r, int g, int b, const int* sdiv, con
   const int h0 = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * d) : (r - g + 4 * d));
   int h = (h0 * hdiv[d] + (1 << 11)) >> 12;     // arithmetic shift, like the C++ original
   h += h < 0 ? 180 : 0;
-  return ((h * 8) / 180) * 64 + (s >> 5) * 8 + (v >> 5);
+  return (((h * 365) >> 13) << 6) | ((s >> 5) << 3) | (v >> 5);     // (h*365)>>13 == h*8/180 for h in [0,180)
 }
 __device__ __forceinline__ int rgb_bin(int r, int g, int b) { return (r >> 5) * 64 + (g >> 5) * 8 + (b >> 5); }
 
@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(kHistThreads) histogram_kernel(const uint8_t* 
 #pragma unroll
       for (int p = 0; p < 16; ++p) {
         const int b0 = p * 3, b1 = b0 + 1, b2 = b0 + 2;
-        const int r = (w[b0 >> 2] >> ((b0 & 3) * 8)) & 0xff;
-        const int g = (w[b1 >> 2] >> ((b1 & 3) * 8)) & 0xff;
-        const int bl = (w[b2 >> 2] >> ((b2 & 3) * 8)) & 0xff;
+        const int r = int(__byte_perm(w[b0 >> 2], 0, 0x4440 | (b0 & 3)));      // one PRMT per byte
+        const int g = int(__byte_perm(w[b1 >> 2], 0, 0x4440 | (b1 & 3)));
+        const int bl = int(__byte_perm(w[b2 >> 2], 0, 0x4440 | (b2 & 3)));
         add_pixel(r, g, bl);
       }
     }
