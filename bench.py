@@ -441,6 +441,28 @@ def run_side(args):
                              "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel_ms": kms,
                              "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}}
         print(json.dumps(line))
+    elif w == "config5":
+        # BASELINE configs[4]: all-pairs evaluation (5 metrics, 4 relationship types, density histograms + PR counts)
+        N = args.rows or 100_000
+        D = args.dim or 512
+        g = torch.Generator(device=dev); g.manual_seed(5001)
+        X = torch.randn((N, D), generator=g, device=dev)
+        ids = torch.arange(N, device=dev) % 30
+        cat, col = (ids // 3).int(), (ids % 3).int()           # 10 categories x 3 colours (imageProcessing.py:60-62)
+        ranges = {"cosine_distance": (0.0, 2.0), "l1_distance": (0.0, 2.0), "l2_distance": (0.0, 2.5),
+                  "linf_distance": (0.0, 8.0), "magnitude_difference": (0.0, 6.0)}
+        ms, kms, launches, clocks = time_fn(lambda: ops.allpairs_eval(X, cat, col, ranges, 1024), 1)
+        pairs = N * (N - 1) / 2
+        lane_ops = pairs * D * 5.25                              # dot, |d|, d^2, max|d| + shared x^2: instructions per element pair
+        peak = 148 * 128 * 1.965e9
+        line = {"metric": f"pairs/sec (all-pairs evaluation, {N}x{N}, D={D}, 5 metrics)", "value": pairs / (ms * 1e-3), "unit": "pairs/s",
+                "n_gpus": 1, "steps": args.steps, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic N(0,1)",
+                "config": {"workload": "configs[4]: all-pairs distance-density + precision-recall counts, five metrics"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "fp32-alu", "kernel": "scan_topk<K_EVAL>", "achieved": lane_ops / (kms * 1e-3) / 1e12,
+                             "peak": peak / 1e12, "unit": "T lane-instr/s", "frac": lane_ops / (kms * 1e-3) / peak, "kernel_ms": kms,
+                             "note": "CUDA-core bound: 5.25 fp32 lane-instructions per element pair; peak = 148 SMs x 128 lanes x 1.965 GHz"}}
+        print(json.dumps(line))
     elif w == "config1":
         from oracle import synth
         qi = torch.from_numpy(synth.images_palette(1000, 224, 224, 1001)).to(dev)

@@ -26,6 +26,7 @@ def units():
     for kind in KINDS:
         for bf in (0, 1):
             u.append((f"scan_{kind}_{'bf16' if bf else 'f32'}", "scan_inst.cu", [f"-DSCAN_KIND={kind}", f"-DSCAN_BF16={bf}"]))
+    u.append(("scan_eval_f32", "scan_inst.cu", ["-DSCAN_KIND=K_EVAL", "-DSCAN_BF16=0", "-DSCAN_EVAL=1"]))
     return [x for x in u if os.path.exists(os.path.join(CSRC, x[1]))]
 
 

@@ -233,6 +233,34 @@ int b200ir_topk_merge_strided(int descending, const float* score, const int64_t*
                           static_cast<cudaStream_t>(stream)));
 }
 
+size_t b200ir_allpairs_eval_workspace_bytes(int64_t N, int D, int nthr) {
+  if (N <= 0 || D <= 0 || nthr < 0) return 0;
+  return allpairs_eval_workspace_bytes(N, D, nthr);
+}
+
+int b200ir_allpairs_eval(const float* X, const int32_t* cat, const int32_t* col, int64_t N, int D, int nbins,
+                         const float* lo_host, const float* hi_host, const double* thresholds_host, int nthr,
+                         uint64_t* hist, uint64_t* thr_counts, void* workspace, size_t workspace_bytes, void* stream) {
+  if (N < 0 || D <= 0 || nbins < 1 || nbins > 1024 || nthr < 0 || nthr > 1024) return B200IR_E_ARG;
+  if (N >= (int64_t(1) << 31)) return B200IR_E_SHAPE;
+  if (!hist || !thr_counts || !lo_host || !hi_host || (nthr > 0 && !thresholds_host)) return B200IR_E_ARG;
+  for (int m = 0; m < 5; ++m) if (!(hi_host[m] > lo_host[m])) return B200IR_E_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N < 2) {
+    cudaError_t e = cudaMemsetAsync(hist, 0, size_t(5) * 4 * nbins * 8, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(thr_counts, 0, size_t(5) * 2 * (nthr + 1) * 8, st);
+    return int(e);
+  }
+  if (!X || !cat || !col) return B200IR_E_ARG;
+  if (reinterpret_cast<uintptr_t>(X) % 4) return B200IR_E_ALIGN;
+  const size_t need = allpairs_eval_workspace_bytes(N, D, nthr);
+  if (!workspace || workspace_bytes < need) return B200IR_E_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return B200IR_E_ALIGN;
+  return int(run_allpairs_eval(X, cat, col, N, D, nbins, lo_host, hi_host, thresholds_host, nthr,
+                               reinterpret_cast<unsigned long long*>(hist), reinterpret_cast<unsigned long long*>(thr_counts),
+                               static_cast<unsigned char*>(workspace), st));
+}
+
 int b200ir_histogram(int colorspace, const uint8_t* img, int64_t B, int H, int W, int bins_per_channel,
                      uint32_t* out_counts, void* stream) {
   if ((colorspace != B200IR_RGB && colorspace != B200IR_HSV) || B < 0 || H <= 0 || W <= 0) return B200IR_E_ARG;

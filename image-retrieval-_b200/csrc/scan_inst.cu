@@ -8,7 +8,9 @@
 #define FN(kind, suffix) CAT3(launch_scan_, kind, suffix)
 
 namespace b200ir {
-#if SCAN_BF16
+#if defined(SCAN_EVAL)
+cudaError_t launch_scan_eval_f32(const ScanArgs& a, size_t smem, cudaStream_t st) { return launch_scan_eval_inst(a, smem, st); }
+#elif SCAN_BF16
 cudaError_t FN(SCAN_KIND, _bf16)(const ScanArgs& a, int TQ, size_t smem, cudaStream_t st) {
   return launch_scan_tq<SCAN_KIND, __nv_bfloat16>(a, TQ, smem, st);
 }

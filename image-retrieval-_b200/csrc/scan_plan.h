@@ -4,7 +4,7 @@
 
 namespace b200ir {
 
-enum ScanKind { K_L1 = 0, K_L2 = 1, K_LINF = 2, K_DOT = 3, K_MULTI = 4 };
+enum ScanKind { K_L1 = 0, K_L2 = 1, K_LINF = 2, K_DOT = 3, K_MULTI = 4, K_EVAL = 5 };
 
 constexpr int kScanThreads = 128;   // == rows per tile (one row per thread)
 constexpr int kScanStages = 3;
@@ -37,7 +37,23 @@ struct ScanArgs {
   uint64_t* partial;      // [nq, P, k] sorted keys            (top-k mode)
   float* out_all;         // [nq, N] metric values, or nullptr  (pairwise mode)
   MetricParams mp;
+  // all-pairs evaluation mode (K_EVAL): queries == database rows, pairs i < j only
+  const int32_t* cat;     // [N] object category of each row
+  const int32_t* col;     // [N] colour of each row
+  unsigned long long* hist;        // [5][4][nbins] counts per (metric, relationship type, bin)
+  unsigned long long* thr_counts;  // [5][2][nthr + 1] first-threshold-index counts for the two same-object labels
+  const double* thresholds;        // [nthr] ascending (device)
+  int nbins, nthr;
+  float lo[5], inv_w[5];           // bin = clamp((v - lo) * inv_w, 0, nbins - 1)
 };
+
+constexpr int kEvalMetrics = 5;    // cosine_distance, l1, l2, linf, magnitude_difference (mi_analysis.py:183-189)
+constexpr int kEvalTQ = 4;
+inline size_t eval_smem_bytes(int nbins, int nthr) {
+  return size_t(kScanStages) * (kScanThreads * kRowChunkBytes + kEvalTQ * 32 * 4) +
+         size_t(kEvalMetrics) * 4 * nbins * 4 + size_t(kEvalMetrics) * 2 * (nthr + 1) * 4 + size_t(nthr) * 8 + 16;
+}
+cudaError_t launch_scan_eval_f32(const ScanArgs& a, size_t smem, cudaStream_t st);
 
 struct ScanPlan {
   int TQ, G, P, sortn, D_pad, nq_pad;
@@ -95,5 +111,10 @@ cudaError_t launch_prep_queries(int dtype, const void* Q, int nq, int D, int nq_
 // Runs prep + scan.  In top-k mode leaves [nq, P, k] sorted keys at ws + plan.off_partial.
 cudaError_t run_scan(const ScanPlan& pl, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D, int k,
                      const MetricParams& mp, unsigned char* ws, float* out_all, cudaStream_t st);
+
+size_t allpairs_eval_workspace_bytes(int64_t N, int D, int nthr);
+cudaError_t run_allpairs_eval(const float* X, const int32_t* cat, const int32_t* col, int64_t N, int D, int nbins,
+                              const float* lo, const float* hi, const double* thresholds_host, int nthr,
+                              unsigned long long* hist, unsigned long long* thr_counts, unsigned char* ws, cudaStream_t st);
 
 }  // namespace b200ir

@@ -43,4 +43,41 @@ cudaError_t run_scan(const ScanPlan& pl, int dtype, const void* Q, int64_t nq, c
   }
 }
 
+size_t allpairs_eval_workspace_bytes(int64_t N, int D, int nthr) {
+  const int D_pad = int(round_up64(D, 32));
+  const int64_t n_pad = round_up64(N, kEvalTQ);
+  return size_t(round_up64(size_t(n_pad) * D_pad * 4, 256)) + size_t(round_up64(size_t(n_pad) * 4, 256)) +
+         size_t(round_up64(size_t(nthr) * 8, 256));
+}
+
+cudaError_t run_allpairs_eval(const float* X, const int32_t* cat, const int32_t* col, int64_t N, int D, int nbins,
+                              const float* lo, const float* hi, const double* thresholds_host, int nthr,
+                              unsigned long long* hist, unsigned long long* thr_counts, unsigned char* ws, cudaStream_t st) {
+  const int D_pad = int(round_up64(D, 32));
+  const int64_t n_pad = round_up64(N, kEvalTQ);
+  size_t off = 0;
+  float* Qf = reinterpret_cast<float*>(ws + off); off += round_up64(size_t(n_pad) * D_pad * 4, 256);
+  float* qn = reinterpret_cast<float*>(ws + off); off += round_up64(size_t(n_pad) * 4, 256);
+  double* thr_d = reinterpret_cast<double*>(ws + off);
+  cudaError_t e = cudaMemcpyAsync(thr_d, thresholds_host, size_t(nthr) * 8, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(hist, 0, size_t(kEvalMetrics) * 4 * nbins * 8, st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(thr_counts, 0, size_t(kEvalMetrics) * 2 * (nthr + 1) * 8, st);
+  if (e != cudaSuccess) return e;
+  e = launch_prep_queries(B200IR_F32, X, int(N), D, int(n_pad), D_pad, Qf, qn, st);
+  if (e != cudaSuccess) return e;
+  ScanArgs a{};
+  a.X = X; a.N = N; a.D = D; a.Qf = Qf; a.qnorm = qn; a.nq = int(N); a.D_pad = D_pad;
+  a.G = int(n_pad / kEvalTQ); a.P = 1; a.rows_per_part = round_up64(N, kScanThreads); a.k = 1; a.sortn = 256;
+  a.aligned = ((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (int64_t(D) * 4) % 16 == 0) ? 1 : 0;
+  a.partial = nullptr;
+  a.out_all = nullptr;
+  a.mp.metric = B200IR_OPTIMIZED; a.mp.flags = 0; a.mp.D = D;
+  a.cat = cat; a.col = col; a.hist = hist; a.thr_counts = thr_counts; a.thresholds = thr_d; a.nbins = nbins; a.nthr = nthr;
+  for (int m = 0; m < kEvalMetrics; ++m) { a.lo[m] = lo[m]; a.inv_w[m] = float(nbins) / (hi[m] - lo[m]); }
+  ProfileScope ps(PT_SCAN, st);
+  return launch_scan_eval_f32(a, eval_smem_bytes(nbins, nthr), st);
+}
+
 }  // namespace b200ir

@@ -63,7 +63,7 @@ __device__ __noinline__ void compact_candidates(uint64_t* keys, int* cnt, uint64
 }
 
 template <int KIND>
-__device__ __forceinline__ void accum(float (&a)[KIND == K_MULTI ? 4 : 1], float x, float q) {
+__device__ __forceinline__ void accum(float (&a)[(KIND == K_MULTI || KIND == K_EVAL) ? 4 : 1], float x, float q) {
   if constexpr (KIND == K_L1) a[0] += fabsf(x - q);
   else if constexpr (KIND == K_L2) { const float d = x - q; a[0] = fmaf(d, d, a[0]); }
   else if constexpr (KIND == K_LINF) a[0] = fmaxf(a[0], fabsf(x - q));
@@ -97,8 +97,8 @@ __device__ __forceinline__ float finish_rank(const float* acc, float xsq, float 
 template <int KIND, typename T, int TQ>
 __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs a) {
   constexpr int DKE = kRowChunkBytes / int(sizeof(T));     // elements of a row per pipeline step
-  constexpr int NA = (KIND == K_MULTI) ? 4 : 1;
-  constexpr bool NEED_XSQ = (KIND == K_DOT || KIND == K_MULTI);
+  constexpr int NA = (KIND == K_MULTI || KIND == K_EVAL) ? 4 : 1;
+  constexpr bool NEED_XSQ = (KIND == K_DOT || KIND == K_MULTI || KIND == K_EVAL);
   constexpr int XT_BYTES = kScanThreads * kRowChunkBytes;  // 16 KB database tile per stage
   constexpr int QC_BYTES = TQ * DKE * 4;                   // fp32 query chunk per stage
   constexpr int STAGE_BYTES = XT_BYTES + QC_BYTES;
@@ -112,8 +112,20 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = blockIdx.x % a.G;
   const int p = blockIdx.x / a.G;
-  const int64_t row_begin = int64_t(p) * a.rows_per_part;
+  int64_t row_begin = int64_t(p) * a.rows_per_part;
   const int64_t row_end = min(a.N, row_begin + a.rows_per_part);
+  // evaluation mode: bins live where the key buffers would be; tiles whose rows are all <= the first query are skipped
+  uint32_t* ev_hist = reinterpret_cast<uint32_t*>(smem + kScanStages * STAGE_BYTES);
+  uint32_t* ev_thr = ev_hist + kEvalMetrics * 4 * (KIND == K_EVAL ? a.nbins : 0);
+  double* ev_thresholds = reinterpret_cast<double*>(ev_thr + kEvalMetrics * 2 * ((KIND == K_EVAL ? a.nthr : 0) + 1) + 2);
+  if constexpr (KIND == K_EVAL) {
+    const int64_t sdiff = int64_t(g) * TQ - row_begin;
+    if (sdiff >= kScanThreads - 1) row_begin += ((sdiff - (kScanThreads - 1)) / kScanThreads + 1) * kScanThreads;
+    if (row_begin > row_end) row_begin = row_end;
+    const int nh = kEvalMetrics * 4 * a.nbins + kEvalMetrics * 2 * (a.nthr + 1);
+    for (int i = tid; i < nh; i += kScanThreads) ev_hist[i] = 0;
+    for (int i = tid; i < a.nthr; i += kScanThreads) ev_thresholds[i] = a.thresholds[i];
+  }
   const int ntiles = int(ceil_div64(row_end - row_begin, kScanThreads));
   const int nchunks = a.D_pad / DKE;
   const int total = ntiles * nchunks;
@@ -121,7 +133,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
   const unsigned char* Xb = static_cast<const unsigned char*>(a.X);
   const int64_t row_bytes = int64_t(a.D) * int64_t(sizeof(T));
 
-  if (tid < TQ) { thr_s[tid] = kKeyInf; cnt_s[tid] = 0; }
+  if (KIND != K_EVAL && tid < TQ) { thr_s[tid] = kKeyInf; cnt_s[tid] = 0; }
 
   // Loader state advances incrementally (no divisions in the steady state).  Thread t copies the 16-byte
   // piece c = t & 7 of rows r0 + 16 i (r0 = t >> 3, i = 0..7): (r & 7) == (r0 & 7) for all of them, so the
@@ -254,6 +266,33 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
 #pragma unroll
       for (int t = 0; t < TQ; ++t) {
         const int q = g * TQ + t;
+        if constexpr (KIND == K_EVAL) {
+          if (valid && q < a.nq && grow > q) {
+            // the five evaluation metrics of mi_analysis.py:183-189 from one pass (geometric_metrics.py:114-129)
+            const float xn = sqrtf(xsq);
+            float cs = 0.f;
+            if (qn[t] != 0.f && xn != 0.f) cs = acc[t][0] / (qn[t] * xn);
+            const float fD = float(a.mp.D);
+            const float vals[kEvalMetrics] = {1.0f - cs, acc[t][1] / fD, sqrtf(acc[t][2]) / sqrtf(fD), acc[t][3], fabsf(qn[t] - xn)};
+            const int rel = (a.cat[q] == a.cat[grow] ? 0 : 2) + (a.col[q] == a.col[grow] ? 0 : 1);   // mi_analysis.py:176-181
+#pragma unroll
+            for (int m = 0; m < kEvalMetrics; ++m) {
+              int bin = int(floorf((vals[m] - a.lo[m]) * a.inv_w[m]));
+              bin = bin < 0 ? 0 : (bin >= a.nbins ? a.nbins - 1 : bin);
+              atomicAdd(&ev_hist[(m * 4 + rel) * a.nbins + bin], 1u);
+              if (rel <= 1) {
+                // first threshold index with d <= threshold (thresholds ascending); nthr = none (mi_analysis.py:783-784)
+                const double dv = double(vals[m]);
+                int lo_i = 0, hi_i = a.nthr;
+                while (lo_i < hi_i) {
+                  const int mid = (lo_i + hi_i) >> 1;
+                  if (dv <= ev_thresholds[mid]) hi_i = mid; else lo_i = mid + 1;
+                }
+                atomicAdd(&ev_thr[(m * 2 + rel) * (a.nthr + 1) + lo_i], 1u);
+              }
+            }
+          }
+        } else
         if (valid && q < a.nq) {
           const float r = finish_rank<KIND>(acc[t], xsq, qn[t], a.mp);
           if (topk_mode) {
@@ -270,7 +309,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
         for (int j = 0; j < NA; ++j) acc[t][j] = 0.f;
       }
       xsq = 0.f;
-      if (topk_mode) {
+      if (KIND != K_EVAL && topk_mode) {
         __syncthreads();
         for (int t = warp; t < TQ; t += kScanThreads / 32) {
           if (cnt_s[t] > a.sortn - kScanThreads) {
@@ -283,6 +322,13 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
   }
   cp_async_wait<0>();
 
+  if constexpr (KIND == K_EVAL) {
+    __syncthreads();
+    const int nh = kEvalMetrics * 4 * a.nbins, nt = kEvalMetrics * 2 * (a.nthr + 1);
+    for (int i = tid; i < nh; i += kScanThreads) if (ev_hist[i]) atomicAdd(&a.hist[i], (unsigned long long)ev_hist[i]);
+    for (int i = tid; i < nt; i += kScanThreads) if (ev_thr[i]) atomicAdd(&a.thr_counts[i], (unsigned long long)ev_thr[i]);
+    return;
+  }
   if (topk_mode) {
     __syncthreads();
     for (int t = warp; t < TQ; t += kScanThreads / 32) {
@@ -306,6 +352,10 @@ inline cudaError_t launch_scan_inst(const ScanArgs& a, size_t smem, cudaStream_t
   if (e != cudaSuccess) return e;
   kern<<<a.G * a.P, kScanThreads, smem, st>>>(a);
   return cudaGetLastError();
+}
+
+inline cudaError_t launch_scan_eval_inst(const ScanArgs& a, size_t smem, cudaStream_t st) {
+  return launch_scan_inst<K_EVAL, float, kEvalTQ>(a, smem, st);
 }
 
 template <int KIND, typename T>

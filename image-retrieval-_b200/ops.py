@@ -202,6 +202,36 @@ def topk_merge_packed(gathered, R, nq, k, score_bytes, descending):
     return out_s, out_i
 
 
+EVAL_METRICS = ("cosine_distance", "l1_distance", "l2_distance", "linf_distance", "magnitude_difference")
+RELATIONSHIP_TYPES = ("same_object_same_color", "same_object_diff_color", "diff_object_same_color", "diff_object_diff_color")
+
+
+def allpairs_eval(X, category, color, ranges, nbins=1024, thresholds=None):
+    """All-pairs evaluation counts (mi_analysis.py:256-297, :704-713, :774-796) over every pair i < j.
+    Returns (hist (5, 4, nbins) int64, thr_counts (5, 2, nthr + 1) int64) device tensors; see include/b200ir.h."""
+    X = as_device_matrix(X, dtype=torch.float32)
+    N, D = X.shape
+    cat = torch.as_tensor(category, dtype=torch.int32).to(X.device).contiguous()
+    col = torch.as_tensor(color, dtype=torch.int32).to(X.device).contiguous()
+    if cat.numel() != N or col.numel() != N:
+        raise ValueError("category / color must have one entry per row")
+    thresholds = np.linspace(0, 1, 100) if thresholds is None else np.asarray(thresholds, dtype=np.float64)
+    nthr = len(thresholds)
+    lo = (ctypes.c_float * 5)(*[float(ranges[m][0]) for m in EVAL_METRICS])
+    hi = (ctypes.c_float * 5)(*[float(ranges[m][1]) for m in EVAL_METRICS])
+    thr = (ctypes.c_double * max(nthr, 1))(*[float(t) for t in thresholds])
+    hist = torch.empty((5, 4, nbins), dtype=torch.int64, device=X.device)
+    thr_counts = torch.empty((5, 2, nthr + 1), dtype=torch.int64, device=X.device)
+    lib = _lib.load()
+    need = lib.b200ir_allpairs_eval_workspace_bytes(N, D, nthr)
+    ws = _workspace(need, X.device)
+    st = lib.b200ir_allpairs_eval(_ptr(X), _ptr(cat), _ptr(col), N, D, nbins, lo, hi, thr, nthr, _ptr(hist), _ptr(thr_counts),
+                                  _ptr(ws), ws.numel(), _stream())
+    _lib.check(st, "allpairs_eval")
+    torch.cuda.current_stream().synchronize()          # thresholds are read from host memory by an async copy
+    return hist, thr_counts
+
+
 def histogram(images, colorspace="rgb"):
     """(B,H,W,3) uint8 RGB -> (B,512) int32 counts on the device (8x8x8 joint bins)."""
     dev = device()

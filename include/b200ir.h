@@ -124,6 +124,26 @@ int b200ir_topk_merge_strided(int descending, const float* score, const int64_t*
                               void* stream);
 
 /*
+ * All-pairs evaluation: the reference's analysis workload (mi_analysis.py:256-297 distances per relationship type,
+ * :704-713 per-metric densities, :774-796 precision / recall threshold counts) over EVERY unordered pair i < j of the
+ * N rows of X [N, D] fp32, without materialising the N x N matrices.
+ *   cat[N], col[N]: object category / colour of each row; relationship type of a pair =
+ *     0 same_object_same_color, 1 same_object_diff_color, 2 diff_object_same_color, 3 diff_object_diff_color
+ *     (mi_analysis.py:176-181).
+ *   metrics, in this order (mi_analysis.py:183-189): cosine_distance, l1_distance, l2_distance (both normalised),
+ *     linf_distance, magnitude_difference - all from one pass, same arithmetic as b200ir_pairwise.
+ *   hist [5][4][nbins] uint64: counts of metric m per relationship type in nbins equal bins of
+ *     [lo_host[m], hi_host[m]) (values outside go to the end bins); nbins <= 1024.
+ *   thr_counts [5][2][nthr + 1] uint64: for the two same-object labels (0 = same colour, 1 = different colour) the
+ *     number of pairs whose FIRST index t with d <= thresholds_host[t] is t (slot nthr: none); thresholds ascending
+ *     doubles (np.linspace(0, 1, 100) in the reference).  Prefix sums give tp / fp / fn of :783-796.
+ */
+size_t b200ir_allpairs_eval_workspace_bytes(int64_t N, int D, int nthr);
+int b200ir_allpairs_eval(const float* X, const int32_t* cat, const int32_t* col, int64_t N, int D, int nbins,
+                         const float* lo_host, const float* hi_host, const double* thresholds_host, int nthr,
+                         uint64_t* hist, uint64_t* thr_counts, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * 512-bin joint colour histogram of uint8 images, img [B, H, W, 3] interleaved RGB,
  * out_counts [B, bins^3] uint32, bin = (c0bin*bins + c1bin)*bins + c2bin with
  * c*bin = c>>5 (H: h*8/180).  bins_per_channel must be 8.  The embedding producer

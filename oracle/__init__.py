@@ -14,6 +14,8 @@ path named by BASELINE.json's north_star:
                    has NO histogram code: parity for this
                    function is UNPINNED by the reference and is pinned against
                    OpenCV (cv2.calcHist / cv2.cvtColor) instead.
+  * evaluation.py- the evaluation workload of mi_analysis.py (relationship types, per-metric
+                   distances, precision / recall threshold counts) on explicit pair lists.
   * synth.py     - seeded synthetic inputs shared by tests and bench.
 
 Pinning: the reference ships no golden vectors or tests for this path
@@ -27,4 +29,4 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this package.  The product package
 (image-retrieval-_b200) never imports it and has no CPU fallback.
 """
-from . import metrics, search, histogram, synth  # noqa: F401
+from . import metrics, search, histogram, synth, evaluation  # noqa: F401

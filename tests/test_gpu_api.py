@@ -112,3 +112,26 @@ def test_embedding_system_and_text_searcher(gold):
         assert [r["path"] for r in multi[name]] == [paths[cand[j]] for j in o], name
     cmp = searcher.compare_search_methods("a query", top_k=3)
     assert set(cmp) == {"standard_results", "optimized_results", "metrics"}
+
+
+def test_allpairs_evaluator_surface():
+    from image_retrieval_b200.mi_eval import AllPairsEvaluator, METRIC_NAMES, RELATIONSHIP_TYPES
+    from oracle import evaluation as E
+    N = 300
+    X = synth.gaussian(N, 32, 3, normalize=True)
+    cat, col = np.arange(N) % 5, (np.arange(N) // 5) % 3
+    ev = AllPairsEvaluator(X, cat, col, nbins=128)
+    h = ev.calculate_distances().cpu().numpy()
+    assert h.shape == (5, 4, 128) and METRIC_NAMES == list(E.METRICS) and RELATIONSHIP_TYPES == list(E.RELATIONSHIP_TYPES)
+    thr, prec, rec = ev.precision_recall("cosine_distance")
+    vals = E.metric_matrices(X, np.float64)
+    rel = E.relationship(cat, col)
+    iu = np.triu_indices(N, 1)
+    sel = rel[iu] <= 1
+    ref = E.pr_curve_reference(list(vals["cosine_distance"][iu][sel]), list((rel[iu][sel] == 1).astype(int)), thr)
+    tp, fp, fn = ref[:, 0], ref[:, 1], ref[:, 2]
+    want_p = np.where(tp + fp > 0, tp / np.maximum(tp + fp, 1), 0.0)
+    want_r = np.where(tp + fn > 0, tp / np.maximum(tp + fn, 1), 0.0)
+    assert np.abs(prec - want_p).max() < 0.02 and np.abs(rec - want_r).max() < 0.02
+    d = ev.densities()
+    assert set(d) == set(METRIC_NAMES) and set(d["l1_distance"]) == set(RELATIONSHIP_TYPES)

@@ -403,3 +403,43 @@ def test_full_size_config3_l1_linf_top10(ops):
         # a second identical call is bit-identical (no atomics-order dependence in the result)
         s2, i2 = ops.topk(Q, X, metric, 10)
         assert torch.equal(i2, i) and torch.equal(s2, s)
+
+
+# ------------------------------------------------------------------------------- all-pairs evaluation (config 5)
+def test_allpairs_eval_counts(ops):
+    """Integer outputs: bit-exact against the oracle's binning of the SAME per-pair values (the pairwise kernel shares
+    the arithmetic), and within a handful of bin-edge flips of the fp64 oracle; PR counts == the reference's loop."""
+    from oracle import evaluation as E
+    N, D, nbins = 777, 96, 256
+    X = synth.gaussian(N, D, 61)
+    X[5] = X[4]                                        # exact duplicate pair: every distance 0
+    cat = np.arange(N) % 10
+    col = (np.arange(N) // 10) % 3
+    ranges = {"cosine_distance": (0.0, 2.0), "l1_distance": (0.0, 2.5), "l2_distance": (0.0, 3.0), "linf_distance": (0.0, 8.0),
+              "magnitude_difference": (0.0, 5.0)}
+    thresholds = np.linspace(0, 1, 100)
+    hist, thr = ops.allpairs_eval(X, cat, col, ranges, nbins, thresholds)
+    hist, thr = hist.cpu().numpy(), thr.cpu().numpy()
+    rel = E.relationship(cat, col)
+    npairs = N * (N - 1) // 2
+    assert hist.sum(axis=(1, 2)).tolist() == [npairs] * 5
+    # same fp32 values (through the pairwise ABI) -> identical counts
+    names = {"cosine_distance": "cosine_distance", "l1_distance": "l1", "l2_distance": "l2", "linf_distance": "linf",
+             "magnitude_difference": "magnitude_difference"}
+    vals = {m: ops.pairwise(X, X, names[m]).cpu().numpy() for m in E.METRICS}
+    # the eval kernel pairs (query i, row j > i); pairwise[i, j] is the same orientation
+    h2, t2 = E.bin_counts(vals, rel, ranges, nbins, thresholds)
+    assert np.abs(hist - h2).sum() <= 10 and np.abs(thr - t2).sum() <= 10          # different TQ grouping: ulp-level flips only
+    # fp64 oracle: only bin-edge flips
+    h3, t3 = E.bin_counts(E.metric_matrices(X, np.float64), rel, ranges, nbins, thresholds)
+    assert np.abs(hist - h3).sum() <= 2e-4 * 5 * npairs + 10
+    assert np.abs(thr - t3).sum() <= 2e-4 * 5 * npairs + 10
+    # precision / recall counts against the reference loop on the GPU's own cosine distances
+    iu = np.triu_indices(N, 1)
+    r = rel[iu]
+    sel = r <= 1
+    ref = E.pr_curve_reference(list(vals["cosine_distance"][iu][sel]), list((r[sel] == 1).astype(int)), thresholds)
+    assert np.abs(E.pr_from_counts(thr[0]) - ref).max() <= 3
+    # relationship-type totals
+    for t in range(4):
+        assert hist[0, t].sum() == int((r == t).sum())

@@ -144,3 +144,30 @@ def test_histogram_vs_opencv(golden_dir):
     assert np.array_equal(ref.astype(np.int64), mine)
     unit, mag = H.embedding(imgs[:2])
     np.testing.assert_allclose(np.linalg.norm(unit, axis=1), 1.0, rtol=1e-6)
+
+
+def test_evaluation_oracle_matches_reference_pr_loop(gold):
+    """oracle.evaluation: prefix sums of first-threshold-index counts == the reference's PR loop (mi_analysis.py:783-796)."""
+    from oracle import evaluation as E
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((40, 16)).astype(np.float32)
+    cat = np.arange(40) % 3
+    col = (np.arange(40) // 3) % 2
+    vals = E.metric_matrices(X, np.float32)
+    rel = E.relationship(cat, col)
+    thresholds = np.linspace(0, 1, 100)
+    ranges = {m: (0.0, 4.0) for m in E.METRICS}
+    hist, thr = E.bin_counts(vals, rel, ranges, 64, thresholds)
+    iu = np.triu_indices(40, 1)
+    assert hist.sum() == 5 * len(iu[0])
+    r = rel[iu]
+    for mi, m in enumerate(E.METRICS):
+        d = vals[m][iu]
+        sel = r <= 1
+        ref = E.pr_curve_reference(list(d[sel]), list((r[sel] == 1).astype(int)), thresholds)
+        assert np.array_equal(E.pr_from_counts(thr[mi]), ref), m
+    # per-pair values are the reference's own get_all_metrics numbers
+    i, j = 3, 17
+    ref = M.get_all_metrics(X[i], X[j])
+    for m in E.METRICS:
+        np.testing.assert_allclose(vals[m][i, j], ref[m], rtol=2e-5, atol=2e-6)
