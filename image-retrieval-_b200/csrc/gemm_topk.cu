@@ -43,7 +43,7 @@ constexpr int SMEM_A = MAX_KB * A_KB_BYTES;  // 128 KB
 constexpr int SMEM_B = B_STAGES * B_STAGE_BYTES;   // 96 KB
 constexpr int SMEM_SCALE = 2 * BN * 4;       // double-buffered per-column scale (rnorm / sqnorm)
 constexpr int SMEM_BARS = 128;
-constexpr int SMEM_CNT = BM * 4;            // per-query candidate counters shared by the two epilogue warps of a quarter
+constexpr int SMEM_CNT = 2 * BM * 2;        // per-query 16-bit candidate counters: front (warp 0 of the quarter) and back (warp 1)
 constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS + SMEM_CNT;   // 232,064 B <= 232,448
 constexpr int THREADS = 384;           // 4 control warps + 8 epilogue warps (two per TMEM lane quarter)
 constexpr int TMEM_COLS = 512;
@@ -158,18 +158,20 @@ __device__ __forceinline__ void import_threshold(const uint32_t* thr_g_q, float&
 // per row of the quarter) because two epilogue warps append to the same list.  If `out` is set the sorted list
 // goes to the unit's output slot instead of back to the scratch list.
 template <int E>
-__device__ __noinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp, int* cnt_q, uint32_t mask, int lane,
+__device__ __noinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp, unsigned short* cnt_q, uint32_t mask, int lane,
                                           uint64_t* out, int64_t out_stride, int valid_lanes, uint32_t* thr_g_warp) {
   while (mask) {
     const int L = __ffs(mask) - 1;
     mask &= mask - 1;
-    const int n = cnt_q[L];
+    // the list is filled from both ends: warp 0 of the quarter appends at [0, n0), warp 1 at (cap - n1, cap]
+    const int n0 = cnt_q[L], n1 = cnt_q[32 + L];
+    const int n = n0 + n1;
     uint64_t* list = warp_lists + size_t(L) * cap;
     uint64_t r[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int i = lane * E + e;
-      r[e] = i < n ? list[i] : kKeyInf;
+      r[e] = i < n0 ? list[i] : (i < n ? list[cap - 1 - (i - n0)] : kKeyInf);
     }
     warp_sort<E>(r, lane);
     if (out == nullptr) {
@@ -184,7 +186,8 @@ __device__ __noinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp,
       for (int e = 0; e < E; ++e) if (e == src_e) kth = r[e];
       kth = shfl_u64(kth, src_lane);
       if (lane == 0) {
-        cnt_q[L] = n < kp ? n : kp;
+        cnt_q[L] = (unsigned short)(n < kp ? n : kp);   // the compacted list lives at the front
+        cnt_q[32 + L] = 0;
         if (n >= kp) atomicMin(thr_g_warp + L, uint32_t(kth >> 32));
       }
     } else if (L < valid_lanes) {
@@ -236,7 +239,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   float* sScale = reinterpret_cast<float*>(smem + SMEM_A + SMEM_B);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_A + SMEM_B + SMEM_SCALE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  int* cnt_s = reinterpret_cast<int*>(smem + SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS);
+  unsigned short* cnt_s = reinterpret_cast<unsigned short*>(smem + SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS);
 
   const uint32_t bar0 = smem_u32(bars);
   auto B_FULL = [&](int s) { return bar0 + 8u * s; };
@@ -361,8 +364,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
     uint64_t* warp_lists = a.cand + (size_t(blockIdx.x) * BM + quarter * 32) * a.cap;
     uint64_t* mylist = warp_lists + size_t(lane) * a.cap;
-    int* cnt_q = cnt_s + quarter * 32;
-    int* mycnt = cnt_q + lane;
+    unsigned short* cnt_q = cnt_s + quarter * 64;          // [32 front counts | 32 back counts]
+    volatile unsigned short* mycnt = cnt_q + half * 32 + lane;
+    const int64_t lstep = half ? -1 : 1;                   // warp 0 fills the list upwards from 0, warp 1 downwards from cap-1
+    uint64_t* const lbase = half ? mylist + a.cap - 1 : mylist;
     const uint32_t tmem_lane = uint32_t(quarter * 32) << 16;
     const bool dbg_me = a.dbg && warp == 4 && lane == 0;
     uint32_t titer = 0;
@@ -370,7 +375,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int qt = unit % a.num_qtiles, p = unit / a.num_qtiles;
       const int q = qt * BM + row;
       float thr = q < a.nq ? -INFINITY : INFINITY;             // padding rows of the last query tile accept nothing
-      if (half == 0) *mycnt = 0;
+      int cnt = 0;                                             // my end of the list (register; published at every barrier)
+      *mycnt = 0;
       pair_sync();
       const int tile0 = p * a.tiles_per_part;
       const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
@@ -422,8 +428,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 int idx = 7;
 #pragma unroll
                 for (int j = 6; j >= 0; --j) idx = (w[j] == gmax) ? j : idx;       // lowest column among equals first
-                const int slot = atomicAdd(mycnt, 1);
-                mylist[slot] = make_key(-gmax, base_idx + uint32_t(chunk * 32 + g8 * 8 + idx));
+                lbase[lstep * cnt] = make_key(-gmax, base_idx + uint32_t(chunk * 32 + g8 * 8 + idx));
+                ++cnt;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) w[j] = (j == idx) ? -INFINITY : w[j];
                 gmax = fmax3(fmax3(w[0], w[1], w[2]), fmax3(w[3], w[4], w[5]), fmaxf(w[6], w[7]));
@@ -431,8 +437,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           // both warps of the quarter finished this chunk pair: at most 64 new entries per list
+          *mycnt = (unsigned short)cnt;
           pair_sync();
-          const uint32_t full = __ballot_sync(0xffffffffu, *reinterpret_cast<volatile int*>(mycnt) > a.cap - 64);
+          const int total = cnt + int(*reinterpret_cast<volatile unsigned short*>(cnt_q + (half ^ 1) * 32 + lane));
+          const uint32_t full = __ballot_sync(0xffffffffu, total > a.cap - 64);
           if (full) {
             const long long tc0 = dbg_me ? clock64() : 0ll;
             const uint32_t mine = alternate_bits(full, half);
@@ -440,7 +448,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             else warp_compact<16>(warp_lists, a.cap, a.kp, cnt_q, mine, lane, nullptr, 0, 32, thr_g_warp);
             pair_sync();
             if ((full >> lane) & 1) {
-              if (*reinterpret_cast<volatile int*>(mycnt) >= a.kp)
+              cnt = int(*mycnt);                                                // kp (or fewer) at the front, 0 at the back
+              if (int(*reinterpret_cast<volatile unsigned short*>(cnt_q + lane)) >= a.kp)
                 thr = fmaxf(thr, -key_rank(*reinterpret_cast<volatile uint64_t*>(mylist + a.kp - 1)));   // accept only v > thr
               import_threshold(thr_g_warp + lane, thr);
             }
