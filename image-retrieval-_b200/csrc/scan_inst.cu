@@ -9,14 +9,14 @@
 
 namespace b200ir {
 #if defined(SCAN_EVAL)
-cudaError_t launch_scan_eval_f32(const ScanArgs& a, size_t smem, cudaStream_t st) { return launch_scan_eval_inst(a, smem, st); }
+cudaError_t launch_scan_eval_f32(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, size_t smem, cudaStream_t st) { return launch_scan_eval_inst(tmX, tmQ, a, smem, st); }
 #elif SCAN_BF16
-cudaError_t FN(SCAN_KIND, _bf16)(const ScanArgs& a, int TQ, size_t smem, cudaStream_t st) {
-  return launch_scan_tq<SCAN_KIND, __nv_bfloat16>(a, TQ, smem, st);
+cudaError_t FN(SCAN_KIND, _bf16)(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, int TQ, size_t smem, cudaStream_t st) {
+  return launch_scan_tq<SCAN_KIND, __nv_bfloat16>(tmX, tmQ, a, TQ, smem, st);
 }
 #else
-cudaError_t FN(SCAN_KIND, _f32)(const ScanArgs& a, int TQ, size_t smem, cudaStream_t st) {
-  return launch_scan_tq<SCAN_KIND, float>(a, TQ, smem, st);
+cudaError_t FN(SCAN_KIND, _f32)(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, int TQ, size_t smem, cudaStream_t st) {
+  return launch_scan_tq<SCAN_KIND, float>(tmX, tmQ, a, TQ, smem, st);
 }
 #endif
 }  // namespace b200ir

@@ -1,6 +1,7 @@
 // Host-side plan of the CUDA-core scan: tiling, partitioning and workspace layout.
 #pragma once
 #include "common.cuh"
+#include "tma_util.h"
 
 namespace b200ir {
 
@@ -34,6 +35,8 @@ struct ScanArgs {
   int k;
   int sortn;              // 256 or 512: capacity of the per-query candidate buffer
   int aligned;            // rows are 16-byte aligned -> cp.async path
+  int use_tma;            // tensor maps valid: one thread issues cp.async.bulk.tensor per stage instead of 9 cp.async per thread
+  int bar_off;            // byte offset of the stage mbarriers in dynamic shared memory
   uint64_t* partial;      // [nq, P, k] sorted keys            (top-k mode)
   float* out_all;         // [nq, N] metric values, or nullptr  (pairwise mode)
   MetricParams mp;
@@ -49,11 +52,16 @@ struct ScanArgs {
 
 constexpr int kEvalMetrics = 5;    // cosine_distance, l1, l2, linf, magnitude_difference (mi_analysis.py:183-189)
 constexpr int kEvalTQ = 4;
-inline size_t eval_smem_bytes(int nbins, int nthr) {
-  return size_t(kScanStages) * (kScanThreads * kRowChunkBytes + kEvalTQ * 32 * 4) +
-         size_t(kEvalMetrics) * 4 * nbins * 4 + size_t(kEvalMetrics) * 2 * (nthr + 1) * 4 + size_t(nthr) * 8 + 16;
+// one pipeline stage: 16 KB database tile + the fp32 query chunk, padded so that every tile stays 1024-byte aligned
+// (required by the 128-byte TMA swizzle)
+inline size_t scan_stage_bytes(int TQ, int DKE) {
+  return size_t(kScanThreads) * kRowChunkBytes + size_t(round_up64(size_t(TQ) * DKE * 4, 1024));
 }
-cudaError_t launch_scan_eval_f32(const ScanArgs& a, size_t smem, cudaStream_t st);
+inline size_t eval_smem_bytes(int nbins, int nthr) {
+  return size_t(kScanStages) * scan_stage_bytes(kEvalTQ, 32) +
+         size_t(kEvalMetrics) * 4 * nbins * 4 + size_t(kEvalMetrics) * 2 * (nthr + 1) * 4 + size_t(nthr) * 8 + 16 + 64;
+}
+cudaError_t launch_scan_eval_f32(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, size_t smem, cudaStream_t st);
 
 struct ScanPlan {
   int TQ, G, P, sortn, D_pad, nq_pad;
@@ -75,8 +83,7 @@ inline ScanPlan make_scan_plan(int metric, int dtype, int64_t nq, int64_t N, int
   pl.nq_pad = pl.G * pl.TQ;
   pl.D_pad = int(round_up64(D, DKE));
   pl.sortn = pairwise ? 256 : scan_sortn(k);
-  pl.smem = size_t(kScanStages) * (kScanThreads * kRowChunkBytes + pl.TQ * DKE * 4)
-            + size_t(pl.TQ) * pl.sortn * 8 + pl.TQ * 16;
+  pl.smem = size_t(kScanStages) * scan_stage_bytes(pl.TQ, DKE) + size_t(pl.TQ) * pl.sortn * 8 + pl.TQ * 16 + 64;
   int ctas_per_sm = int((227 * 1024) / (pl.smem + 1024));      // 1 KB per resident CTA is reserved by the driver
   ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
   const int64_t target = int64_t(kNumSMs) * ctas_per_sm;
@@ -100,8 +107,8 @@ inline ScanPlan make_scan_plan(int metric, int dtype, int64_t nq, int64_t N, int
 
 // one translation unit per (kind, dtype): scan_inst.cu compiled with -DSCAN_KIND / -DSCAN_BF16
 #define B200IR_DECL_SCAN(kind) \
-  cudaError_t launch_scan_##kind##_f32(const ScanArgs& a, int TQ, size_t smem, cudaStream_t st); \
-  cudaError_t launch_scan_##kind##_bf16(const ScanArgs& a, int TQ, size_t smem, cudaStream_t st);
+  cudaError_t launch_scan_##kind##_f32(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, int TQ, size_t smem, cudaStream_t st); \
+  cudaError_t launch_scan_##kind##_bf16(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, int TQ, size_t smem, cudaStream_t st);
 B200IR_DECL_SCAN(K_L1) B200IR_DECL_SCAN(K_L2) B200IR_DECL_SCAN(K_LINF) B200IR_DECL_SCAN(K_DOT) B200IR_DECL_SCAN(K_MULTI)
 #undef B200IR_DECL_SCAN
 

@@ -2,6 +2,8 @@
 #include "scan_topk.cuh"
 #include "profile.h"
 
+#include <cstring>
+
 namespace b200ir {
 
 cudaError_t launch_prep_queries(int dtype, const void* Q, int nq, int D, int nq_pad, int D_pad, float* Qf, float* qn,
@@ -14,6 +16,22 @@ cudaError_t launch_prep_queries(int dtype, const void* Q, int nq, int D, int nq_
   else
     prep_queries_kernel<__nv_bfloat16><<<blocks, warps_per_block * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(Q), nq, D, nq_pad, D_pad, Qf, qn);
   return cudaGetLastError();
+}
+
+// Tensor maps of the database shard (128-row x 128-byte boxes, 128-byte swizzle) and of the prepared fp32 queries
+// (TQ-row boxes).  Falls back to the cp.async loader (use_tma = 0) when rows are not 16-byte aligned or the driver
+// entry point is unavailable.
+static void setup_tma(ScanArgs& a, int dtype, int TQ, int nq_pad, size_t smem, CUtensorMap* tmX, CUtensorMap* tmQ) {
+  memset(tmX, 0, sizeof(*tmX));
+  memset(tmQ, 0, sizeof(*tmQ));
+  a.bar_off = int(smem) - 64;
+  a.use_tma = 0;
+  if (!a.aligned || a.N <= 0) return;
+  const int esz = dtype == B200IR_F32 ? 4 : 2;
+  const int DKE = kRowChunkBytes / esz;
+  if (!tma::encode_2d(tmX, esz, dtype == B200IR_BF16, a.X, a.N, a.D, int64_t(a.D) * esz, DKE, kScanThreads, true)) return;
+  if (!tma::encode_2d(tmQ, 4, false, a.Qf, nq_pad, a.D_pad, int64_t(a.D_pad) * 4, DKE, TQ, false)) return;
+  a.use_tma = 1;
 }
 
 cudaError_t run_scan(const ScanPlan& pl, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D, int k,
@@ -32,13 +50,15 @@ cudaError_t run_scan(const ScanPlan& pl, int dtype, const void* Q, int64_t nq, c
   a.out_all = out_all;
   a.mp = mp;
   const bool f32 = dtype == B200IR_F32;
+  CUtensorMap tmX, tmQ;
+  setup_tma(a, dtype, pl.TQ, pl.nq_pad, pl.smem, &tmX, &tmQ);
   ProfileScope ps(PT_SCAN, st);
   switch (scan_kind_of(mp.metric)) {
-    case K_L1:    return f32 ? launch_scan_K_L1_f32(a, pl.TQ, pl.smem, st)    : launch_scan_K_L1_bf16(a, pl.TQ, pl.smem, st);
-    case K_L2:    return f32 ? launch_scan_K_L2_f32(a, pl.TQ, pl.smem, st)    : launch_scan_K_L2_bf16(a, pl.TQ, pl.smem, st);
-    case K_LINF:  return f32 ? launch_scan_K_LINF_f32(a, pl.TQ, pl.smem, st)  : launch_scan_K_LINF_bf16(a, pl.TQ, pl.smem, st);
-    case K_DOT:   return f32 ? launch_scan_K_DOT_f32(a, pl.TQ, pl.smem, st)   : launch_scan_K_DOT_bf16(a, pl.TQ, pl.smem, st);
-    case K_MULTI: return f32 ? launch_scan_K_MULTI_f32(a, pl.TQ, pl.smem, st) : launch_scan_K_MULTI_bf16(a, pl.TQ, pl.smem, st);
+    case K_L1:    return f32 ? launch_scan_K_L1_f32(tmX, tmQ, a, pl.TQ, pl.smem, st)    : launch_scan_K_L1_bf16(tmX, tmQ, a, pl.TQ, pl.smem, st);
+    case K_L2:    return f32 ? launch_scan_K_L2_f32(tmX, tmQ, a, pl.TQ, pl.smem, st)    : launch_scan_K_L2_bf16(tmX, tmQ, a, pl.TQ, pl.smem, st);
+    case K_LINF:  return f32 ? launch_scan_K_LINF_f32(tmX, tmQ, a, pl.TQ, pl.smem, st)  : launch_scan_K_LINF_bf16(tmX, tmQ, a, pl.TQ, pl.smem, st);
+    case K_DOT:   return f32 ? launch_scan_K_DOT_f32(tmX, tmQ, a, pl.TQ, pl.smem, st)   : launch_scan_K_DOT_bf16(tmX, tmQ, a, pl.TQ, pl.smem, st);
+    case K_MULTI: return f32 ? launch_scan_K_MULTI_f32(tmX, tmQ, a, pl.TQ, pl.smem, st) : launch_scan_K_MULTI_bf16(tmX, tmQ, a, pl.TQ, pl.smem, st);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -76,8 +96,11 @@ cudaError_t run_allpairs_eval(const float* X, const int32_t* cat, const int32_t*
   a.mp.metric = B200IR_OPTIMIZED; a.mp.flags = 0; a.mp.D = D;
   a.cat = cat; a.col = col; a.hist = hist; a.thr_counts = thr_counts; a.thresholds = thr_d; a.nbins = nbins; a.nthr = nthr;
   for (int m = 0; m < kEvalMetrics; ++m) { a.lo[m] = lo[m]; a.inv_w[m] = float(nbins) / (hi[m] - lo[m]); }
+  CUtensorMap tmX, tmQ;
+  const size_t smem = eval_smem_bytes(nbins, nthr);
+  setup_tma(a, B200IR_F32, kEvalTQ, int(n_pad), smem, &tmX, &tmQ);
   ProfileScope ps(PT_SCAN, st);
-  return launch_scan_eval_f32(a, eval_smem_bytes(nbins, nthr), st);
+  return launch_scan_eval_f32(tmX, tmQ, a, smem, st);
 }
 
 }  // namespace b200ir

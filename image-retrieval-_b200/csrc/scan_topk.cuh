@@ -95,13 +95,14 @@ __device__ __forceinline__ float finish_rank(const float* acc, float xsq, float 
 }
 
 template <int KIND, typename T, int TQ>
-__global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                 const __grid_constant__ CUtensorMap tmQ, const ScanArgs a) {
   constexpr int DKE = kRowChunkBytes / int(sizeof(T));     // elements of a row per pipeline step
   constexpr int NA = (KIND == K_MULTI || KIND == K_EVAL) ? 4 : 1;
   constexpr bool NEED_XSQ = (KIND == K_DOT || KIND == K_MULTI || KIND == K_EVAL);
   constexpr int XT_BYTES = kScanThreads * kRowChunkBytes;  // 16 KB database tile per stage
   constexpr int QC_BYTES = TQ * DKE * 4;                   // fp32 query chunk per stage
-  constexpr int STAGE_BYTES = XT_BYTES + QC_BYTES;
+  constexpr int STAGE_BYTES = XT_BYTES + (QC_BYTES + 1023) / 1024 * 1024;   // tiles stay 1024-byte aligned (TMA swizzle)
 
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* stage_base = smem;
@@ -145,8 +146,36 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
   const float* ld_q = a.Qf + int64_t(g * TQ + tid / (DKE / 4)) * a.D_pad + (tid % (DKE / 4)) * 4;
   const uint32_t ld_qdst = uint32_t(XT_BYTES + ((tid / (DKE / 4)) * DKE + (tid % (DKE / 4)) * 4) * 4);
   int iss_tile = 0, iss_chunk = 0, iss_stage = 0;
+  // TMA path: stage `s` completes on mbarrier full[s] (transaction bytes of the tile box + the query box)
+  const uint32_t full_bar0 = smem_u32(smem + a.bar_off);
+  if (a.use_tma) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    if (tid == 0) {
+      for (int s = 0; s < kScanStages; ++s) tma::mbar_init(full_bar0 + 8u * s, 1);
+      tma::mbar_fence_init();
+      tma::prefetch_desc(&tmX);
+      tma::prefetch_desc(&tmQ);
+    }
+    __syncthreads();
+  }
 
   auto issue = [&]() {
+    if (a.use_tma) {
+      // one elected thread: two bulk tensor copies per stage; the hardware applies the same 16-byte XOR swizzle and
+      // zero-fills rows past N / columns past D
+      if (iss_tile < ntiles) {
+        if (tid == 0) {
+          const uint32_t sbu = smem_u32(stage_base + iss_stage * STAGE_BYTES);
+          const uint32_t bar = full_bar0 + 8u * iss_stage;
+          tma::mbar_expect_tx(bar, XT_BYTES + QC_BYTES);
+          tma::load_2d(sbu, &tmX, bar, iss_chunk * DKE, int(row_begin + int64_t(iss_tile) * kScanThreads));
+          tma::load_2d(sbu + XT_BYTES, &tmQ, bar, iss_chunk * DKE, g * TQ);
+        }
+        if (++iss_chunk == nchunks) { iss_chunk = 0; ++iss_tile; }
+        if (++iss_stage == kScanStages) iss_stage = 0;
+      }
+      return;
+    }
     if (iss_tile < ntiles) {
       unsigned char* sb = stage_base + iss_stage * STAGE_BYTES;
       const uint32_t sbu = smem_u32(sb);
@@ -202,9 +231,15 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
 
   int tile = 0, chunk = 0, stage = 0;
   for (int it = 0; it < total; ++it) {
-    cp_async_wait<kScanStages - 2>();
-    __syncthreads();
-    issue();
+    if (a.use_tma) {
+      __syncthreads();                       // everyone is done with the stage that is refilled next
+      issue();
+      tma::mbar_wait(full_bar0 + 8u * stage, (it / kScanStages) & 1);
+    } else {
+      cp_async_wait<kScanStages - 2>();
+      __syncthreads();
+      issue();
+    }
 
     const unsigned char* sb = stage_base + stage * STAGE_BYTES;
     if (++stage == kScanStages) stage = 0;
@@ -346,25 +381,25 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanArgs 
 
 
 template <int KIND, typename T, int TQ>
-inline cudaError_t launch_scan_inst(const ScanArgs& a, size_t smem, cudaStream_t st) {
+inline cudaError_t launch_scan_inst(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, size_t smem, cudaStream_t st) {
   auto kern = scan_topk_kernel<KIND, T, TQ>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
-  kern<<<a.G * a.P, kScanThreads, smem, st>>>(a);
+  kern<<<a.G * a.P, kScanThreads, smem, st>>>(tmX, tmQ, a);
   return cudaGetLastError();
 }
 
-inline cudaError_t launch_scan_eval_inst(const ScanArgs& a, size_t smem, cudaStream_t st) {
-  return launch_scan_inst<K_EVAL, float, kEvalTQ>(a, smem, st);
+inline cudaError_t launch_scan_eval_inst(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, size_t smem, cudaStream_t st) {
+  return launch_scan_inst<K_EVAL, float, kEvalTQ>(tmX, tmQ, a, smem, st);
 }
 
 template <int KIND, typename T>
-inline cudaError_t launch_scan_tq(const ScanArgs& a, int TQ, size_t smem, cudaStream_t st) {
+inline cudaError_t launch_scan_tq(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, int TQ, size_t smem, cudaStream_t st) {
   switch (TQ) {
-    case 1: return launch_scan_inst<KIND, T, 1>(a, smem, st);
-    case 4: return launch_scan_inst<KIND, T, 4>(a, smem, st);
+    case 1: return launch_scan_inst<KIND, T, 1>(tmX, tmQ, a, smem, st);
+    case 4: return launch_scan_inst<KIND, T, 4>(tmX, tmQ, a, smem, st);
     case 8:
-      if constexpr (KIND != K_MULTI) return launch_scan_inst<KIND, T, 8>(a, smem, st);
+      if constexpr (KIND != K_MULTI) return launch_scan_inst<KIND, T, 8>(tmX, tmQ, a, smem, st);
     default: return cudaErrorInvalidValue;
   }
 }
