@@ -139,7 +139,7 @@ def cpu_port_baseline(Qh, Xh, k, budget_s=20.0):
     from oracle import search as OS
     nq = 16
     t0 = time.perf_counter()
-    OS.topk_search(Qh[:nq], Xh, "cosine_similarity", k, dtype=np.float32)
+    _first_v, first_i = OS.topk_search(Qh[:nq], Xh, "cosine_similarity", k, dtype=np.float32)
     dt = time.perf_counter() - t0
     done = nq
     if dt < budget_s / 3:
@@ -150,7 +150,7 @@ def cpu_port_baseline(Qh, Xh, k, budget_s=20.0):
         done = nq2
     return {"value": done / dt, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"{done} of {len(Qh)} queries vs the full {Xh.shape[0]}x{Xh.shape[1]} fp32 database, "
-                      f"NumPy sgemm + stable argsort (oracle.search.topk_search), {dt:.1f} s"}
+                      f"NumPy sgemm + stable argsort (oracle.search.topk_search), {dt:.1f} s"}, first_i
 
 
 def _ref_loop_worker(args):
@@ -333,19 +333,17 @@ def run_headline(args):
                     "traffic": traffic, "kernel_ms": kern[dom], "kernels_ms": kern,
                     "algorithmic_flops_per_launch": flops, "peak_source": pk["_source"] + ", sustained bf16 (kernel timed inside back-to-back steps)"}
 
-    # parity spot-check of the timed result against the oracle (bounded: 8 queries, fp64 truth)
-    from oracle import metrics as OM
-    from oracle import search as OS
-    qs = Q[:8].float().cpu().numpy()
-    truth = OM.pairwise_f64(qs, X.float().cpu().numpy(), "cosine_similarity")
-    _tv, ti = OS.topk(truth, TOPK, True)
-    parity = None
-    if world == 1:
-        got = i_dev[:8].cpu().numpy()
-        parity = {"queries_checked": 8, "index_sets_equal": bool(all(set(a) == set(b) for a, b in zip(got, ti))),
-                  "ranks_equal_frac": float((got == ti).mean())}
-
-    cpu = cpu_port_baseline(Q.float().cpu().numpy(), X.float().cpu().numpy(), TOPK) if not args.no_cpu else None
+    # CPU leg (the only place the oracle runs in this arm): the vectorised port is timed on a bounded query sample, and
+    # its answer for the first 16 queries doubles as a parity spot-check of the timed GPU result
+    cpu, parity = None, None
+    if not args.no_cpu:
+        cpu, ref_i = cpu_port_baseline(Q.float().cpu().numpy(), X.float().cpu().numpy(), TOPK)
+        if world == 1:
+            got = i_dev[:len(ref_i)].cpu().numpy()
+            parity = {"queries_checked": int(len(ref_i)),
+                      "index_sets_equal": bool(all(set(a_) == set(b_) for a_, b_ in zip(got, ref_i))),
+                      "ranks_equal_frac": float((got == ref_i).mean()),
+                      "note": "GPU (fp32 re-rank) vs NumPy fp32 port; rank swaps only between fp32-equal scores"}
     total_rows = ROWS_PER_GPU * world
     scale = total_rows / 1e6
     h2d = NQ * DIM * 2
@@ -464,9 +462,15 @@ def run_side(args):
                              "note": "CUDA-core bound: 5.25 fp32 lane-instructions per element pair; peak = 148 SMs x 128 lanes x 1.965 GHz"}}
         print(json.dumps(line))
     elif w == "config1":
-        from oracle import synth
-        qi = torch.from_numpy(synth.images_palette(1000, 224, 224, 1001)).to(dev)
-        di = torch.from_numpy(synth.images_palette(10000, 224, 224, 1002)).to(dev)
+        def palette_images(b, seed):
+            """a few flat colour blocks + small noise per image: peaky histograms with many exact ties"""
+            g = torch.Generator(device=dev); g.manual_seed(seed)
+            blocks = torch.randint(0, 256, (b, 4, 4, 3), generator=g, device=dev)
+            img = blocks.repeat_interleave(56, dim=1).repeat_interleave(56, dim=2)
+            noise = torch.randint(-8, 9, (b, 224, 224, 3), generator=g, device=dev)
+            return (img + noise).clamp_(0, 255).to(torch.uint8)
+        qi = palette_images(1000, 1001)
+        di = palette_images(10000, 1002)
 
         def fn():
             X = ops.counts_to_embedding(ops.histogram(di))[0]
