@@ -384,7 +384,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       import_threshold(thr_g_warp + lane, thr);
       for (int t = tile0; t < tile1; ++t, ++titer) {
         const int buf = titer & 1;
-        if (((t - tile0) & 15) == 15) import_threshold(thr_g_warp + lane, thr);
+        if (((t - tile0) & 7) == 7) import_threshold(thr_g_warp + lane, thr);      // other units' published thresholds
         long long t0 = dbg_me ? clock64() : 0ll;
         mbar_wait(S_FULL(buf), (titer >> 1) & 1);
         mbar_wait(T_FULL(buf), (titer >> 1) & 1);
@@ -451,7 +451,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               cnt = int(*mycnt);                                                // kp (or fewer) at the front, 0 at the back
               if (int(*reinterpret_cast<volatile unsigned short*>(cnt_q + lane)) >= a.kp)
                 thr = fmaxf(thr, -key_rank(*reinterpret_cast<volatile uint64_t*>(mylist + a.kp - 1)));   // accept only v > thr
-              import_threshold(thr_g_warp + lane, thr);
             }
             if (dbg_me) { tcomp += clock64() - tc0; a.dbg[blockIdx.x * 16 + 12] += __popc(full); }
           }
