@@ -158,47 +158,55 @@ __device__ __forceinline__ void import_threshold(const uint32_t* thr_g_q, float&
 // per row of the quarter) because two epilogue warps append to the same list.  If `out` is set the sorted list
 // goes to the unit's output slot instead of back to the scratch list.
 template <int E>
-__device__ __noinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp, unsigned short* cnt_q, uint32_t mask, int lane,
-                                          uint64_t* out, int64_t out_stride, int valid_lanes, uint32_t* thr_g_warp) {
+__device__ __noinline__ void compact_one(uint64_t* list, int cap, int kp, int n0, int n1, unsigned short* cnt_front,
+                                         unsigned short* cnt_back, int lane, uint64_t* dst, uint32_t* thr_g_q) {
+  // the list is filled from both ends: warp 0 of the quarter appends at [0, n0), warp 1 at (cap - n1, cap]
+  const int n = n0 + n1;
+  uint64_t r[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    r[e] = i < n0 ? list[i] : (i < n ? list[cap - 1 - (i - n0)] : kKeyInf);
+  }
+  warp_sort<E>(r, lane);
+  uint64_t* out = dst ? dst : list;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    if (i < kp) out[i] = r[e];
+  }
+  if (dst == nullptr) {
+    const int src_lane = (kp - 1) / E, src_e = (kp - 1) % E;
+    uint64_t kth = kKeyInf;
+#pragma unroll
+    for (int e = 0; e < E; ++e) if (e == src_e) kth = r[e];
+    kth = shfl_u64(kth, src_lane);
+    if (lane == 0) {
+      *cnt_front = (unsigned short)(n < kp ? n : kp);   // the compacted list lives at the front
+      *cnt_back = 0;
+      if (n >= kp) atomicMin(thr_g_q, uint32_t(kth >> 32));
+    }
+  }
+  __syncwarp();
+}
+
+// Warp-cooperative compaction of the candidate lists of the query rows in `mask` (bit L = row L of this TMEM lane
+// quarter): sort, keep the best kp, publish the k'-th rank value.  The sorter width follows the list length.
+// If `out` is set the sorted list goes to the unit's output slot instead of back to the scratch list.
+__device__ __forceinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp, unsigned short* cnt_q, uint32_t mask, int lane,
+                                             uint64_t* out, int64_t out_stride, int valid_lanes, uint32_t* thr_g_warp) {
   while (mask) {
     const int L = __ffs(mask) - 1;
     mask &= mask - 1;
-    // the list is filled from both ends: warp 0 of the quarter appends at [0, n0), warp 1 at (cap - n1, cap]
     const int n0 = cnt_q[L], n1 = cnt_q[32 + L];
-    const int n = n0 + n1;
     uint64_t* list = warp_lists + size_t(L) * cap;
-    uint64_t r[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int i = lane * E + e;
-      r[e] = i < n0 ? list[i] : (i < n ? list[cap - 1 - (i - n0)] : kKeyInf);
+    uint64_t* dst = nullptr;
+    if (out != nullptr) {
+      if (L >= valid_lanes) continue;
+      dst = out + int64_t(L) * out_stride;
     }
-    warp_sort<E>(r, lane);
-    if (out == nullptr) {
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int i = lane * E + e;
-        if (i < kp) list[i] = r[e];
-      }
-      const int src_lane = (kp - 1) / E, src_e = (kp - 1) % E;
-      uint64_t kth = kKeyInf;
-#pragma unroll
-      for (int e = 0; e < E; ++e) if (e == src_e) kth = r[e];
-      kth = shfl_u64(kth, src_lane);
-      if (lane == 0) {
-        cnt_q[L] = (unsigned short)(n < kp ? n : kp);   // the compacted list lives at the front
-        cnt_q[32 + L] = 0;
-        if (n >= kp) atomicMin(thr_g_warp + L, uint32_t(kth >> 32));
-      }
-    } else if (L < valid_lanes) {
-      uint64_t* dst = out + int64_t(L) * out_stride;
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int i = lane * E + e;
-        if (i < kp) dst[i] = r[e];
-      }
-    }
-    __syncwarp();
+    if (n0 + n1 <= 256) compact_one<8>(list, cap, kp, n0, n1, cnt_q + L, cnt_q + 32 + L, lane, dst, thr_g_warp + L);
+    else compact_one<16>(list, cap, kp, n0, n1, cnt_q + L, cnt_q + 32 + L, lane, dst, thr_g_warp + L);
   }
 }
 
@@ -370,26 +378,59 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* const lbase = half ? mylist + a.cap - 1 : mylist;
     const uint32_t tmem_lane = uint32_t(quarter * 32) << 16;
     const bool dbg_me = a.dbg && warp == 4 && lane == 0;
+    // tile mode: lists are checked once per tile and compacted when longer than tile_limit (<= 256 keys: the narrow
+    // sorter is enough in the common case); a tile adds at most BN entries, so tile_limit + BN must fit the list
+    const int tile_limit = max(a.kp + 64, 192);
+    const bool tile_mode = tile_limit + BN <= a.cap;
+    float thr = 0.f;
+    int cnt = 0;
+    uint32_t* thr_g_warp = a.thr_g;
+    // publish my end's counter, meet the partner warp, compact every list longer than `limit` (lists split between
+    // the two warps), pick up the new thresholds
+    auto check_and_compact = [&](int limit, long long& tcomp) {
+      *mycnt = (unsigned short)cnt;
+      pair_sync();
+      const int total = cnt + int(*reinterpret_cast<volatile unsigned short*>(cnt_q + (half ^ 1) * 32 + lane));
+      const uint32_t full = __ballot_sync(0xffffffffu, total > limit);
+      if (full) {
+        const long long tc0 = dbg_me ? clock64() : 0ll;
+        const uint32_t mine = alternate_bits(full, half);
+        warp_compact(warp_lists, a.cap, a.kp, cnt_q, mine, lane, nullptr, 0, 32, thr_g_warp);
+        pair_sync();
+        if ((full >> lane) & 1) {
+          cnt = int(*mycnt);                                                // kp (or fewer) at the front, 0 at the back
+          if (int(*reinterpret_cast<volatile unsigned short*>(cnt_q + lane)) >= a.kp)
+            thr = fmaxf(thr, -key_rank(*reinterpret_cast<volatile uint64_t*>(mylist + a.kp - 1)));   // accept only v > thr
+        }
+        if (dbg_me) { tcomp += clock64() - tc0; a.dbg[blockIdx.x * 16 + 12] += __popc(full); }
+      }
+    };
     uint32_t titer = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int qt = unit % a.num_qtiles, p = unit / a.num_qtiles;
       const int q = qt * BM + row;
-      float thr = q < a.nq ? -INFINITY : INFINITY;             // padding rows of the last query tile accept nothing
-      int cnt = 0;                                             // my end of the list (register; published at every barrier)
+      thr = q < a.nq ? -INFINITY : INFINITY;                   // padding rows of the last query tile accept nothing
+      cnt = 0;                                                 // my end of the list (register; published at every barrier)
       *mycnt = 0;
       pair_sync();
       const int tile0 = p * a.tiles_per_part;
       const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
-      uint32_t* thr_g_warp = a.thr_g + qt * BM + quarter * 32;
+      thr_g_warp = a.thr_g + qt * BM + quarter * 32;
       import_threshold(thr_g_warp + lane, thr);
       for (int t = tile0; t < tile1; ++t, ++titer) {
         const int buf = titer & 1;
         if (((t - tile0) & 7) == 7) import_threshold(thr_g_warp + lane, thr);      // other units' published thresholds
+        long long tcomp = 0;
+        if (tile_mode) {
+          // compaction check once per tile, BEFORE waiting for the accumulator: both TMEM buffers are released, so the
+          // MMAs of the next two tiles run while the lists are sorted.  A tile adds at most 256 entries per list.
+          check_and_compact(tile_limit, tcomp);
+          if (dbg_me) { a.dbg[blockIdx.x * 16 + 9] += (unsigned long long)tcomp; tcomp = 0; }
+        }
         long long t0 = dbg_me ? clock64() : 0ll;
         mbar_wait(S_FULL(buf), (titer >> 1) & 1);
         mbar_wait(T_FULL(buf), (titer >> 1) & 1);
         if (dbg_me) { a.dbg[blockIdx.x * 16 + 7] += (unsigned long long)(clock64() - t0); t0 = clock64(); }
-        long long tcomp = 0;
         tc_fence_after();
         const float* sc = sScale + buf * BN;
         const uint32_t base_idx = uint32_t(t) * BN;
@@ -436,24 +477,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
-          // both warps of the quarter finished this chunk pair: at most 64 new entries per list
-          *mycnt = (unsigned short)cnt;
-          pair_sync();
-          const int total = cnt + int(*reinterpret_cast<volatile unsigned short*>(cnt_q + (half ^ 1) * 32 + lane));
-          const uint32_t full = __ballot_sync(0xffffffffu, total > a.cap - 64);
-          if (full) {
-            const long long tc0 = dbg_me ? clock64() : 0ll;
-            const uint32_t mine = alternate_bits(full, half);
-            if (a.cap == 256) warp_compact<8>(warp_lists, a.cap, a.kp, cnt_q, mine, lane, nullptr, 0, 32, thr_g_warp);
-            else warp_compact<16>(warp_lists, a.cap, a.kp, cnt_q, mine, lane, nullptr, 0, 32, thr_g_warp);
-            pair_sync();
-            if ((full >> lane) & 1) {
-              cnt = int(*mycnt);                                                // kp (or fewer) at the front, 0 at the back
-              if (int(*reinterpret_cast<volatile unsigned short*>(cnt_q + lane)) >= a.kp)
-                thr = fmaxf(thr, -key_rank(*reinterpret_cast<volatile uint64_t*>(mylist + a.kp - 1)));   // accept only v > thr
-            }
-            if (dbg_me) { tcomp += clock64() - tc0; a.dbg[blockIdx.x * 16 + 12] += __popc(full); }
-          }
+          // large k' (not enough room for a whole tile of candidates): check after every chunk pair instead
+          if (!tile_mode) check_and_compact(a.cap - 64, tcomp);
         }
         tc_fence_before();
         __syncwarp();
@@ -466,13 +491,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       // end of unit: emit the best kp keys of every valid query row of this quarter (rows split between the warps)
       const long long te0 = dbg_me ? clock64() : 0ll;
+      *mycnt = (unsigned short)cnt;
+      pair_sync();
       const int q0 = qt * BM + quarter * 32;
       const int valid = min(32, a.nq - q0);
       if (valid > 0) {
         uint64_t* out = a.partial + (int64_t(q0) * a.P + p) * a.kp;
         const uint32_t mine = half ? 0xffff0000u : 0x0000ffffu;
-        if (a.cap == 256) warp_compact<8>(warp_lists, a.cap, a.kp, cnt_q, mine, lane, out, int64_t(a.P) * a.kp, valid, thr_g_warp);
-        else warp_compact<16>(warp_lists, a.cap, a.kp, cnt_q, mine, lane, out, int64_t(a.P) * a.kp, valid, thr_g_warp);
+        warp_compact(warp_lists, a.cap, a.kp, cnt_q, mine, lane, out, int64_t(a.P) * a.kp, valid, thr_g_warp);
       }
       pair_sync();                                             // lists and counters may be reused by the next unit
       if (dbg_me) a.dbg[blockIdx.x * 16 + 10] += (unsigned long long)(clock64() - te0);
@@ -676,7 +702,7 @@ static Plan make_plan(int64_t nq, int64_t N, int D, int k, int flags, int sms) {
   pl.num_qtiles = int(ceil_div64(nq, BM));
   pl.total_tiles = int(ceil_div64(N, BN));
   const bool rerank = !(flags & B200IR_FLAG_NO_RERANK);
-  pl.cap = k <= 112 ? 256 : 512;
+  pl.cap = 512;
   int kp = k;
   if (rerank) { kp = k + (k / 16 > 4 ? k / 16 : 4); kp = (kp + 3) / 4 * 4; }
   if (kp > pl.cap / 2) kp = pl.cap / 2;
@@ -800,7 +826,7 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
     const int blocks = int(ceil_div64(nq, 4));
     const __nv_bfloat16* Qb = static_cast<const __nv_bfloat16*>(Q);
     const __nv_bfloat16* Xb = static_cast<const __nv_bfloat16*>(X);
-    if (pl.cap == 256)
+    if (pl.kp <= 128)
       gemm_finalize_kernel<8><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, out_score, out_idx);
     else
       gemm_finalize_kernel<16><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, out_score, out_idx);

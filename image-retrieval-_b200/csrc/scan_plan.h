@@ -51,7 +51,7 @@ struct ScanArgs {
 };
 
 constexpr int kEvalMetrics = 5;    // cosine_distance, l1, l2, linf, magnitude_difference (mi_analysis.py:183-189)
-constexpr int kEvalTQ = 4;
+constexpr int kEvalTQ = 8;
 // one pipeline stage: 16 KB database tile + the fp32 query chunk, padded so that every tile stays 1024-byte aligned
 // (required by the 128-byte TMA swizzle)
 inline size_t scan_stage_bytes(int TQ, int DKE) {
@@ -77,7 +77,8 @@ inline ScanPlan make_scan_plan(int metric, int dtype, int64_t nq, int64_t N, int
   const int kind = scan_kind_of(metric);
   const int esz = dtype == B200IR_F32 ? 4 : 2;
   const int DKE = kRowChunkBytes / esz;
-  const int tq_max = (kind == K_MULTI) ? 4 : 8;
+  const int tq_max = 8;
+  (void)kind;
   pl.TQ = nq <= 1 ? 1 : (nq <= 4 ? 4 : tq_max);
   pl.G = int(ceil_div64(nq, pl.TQ));
   pl.nq_pad = pl.G * pl.TQ;

@@ -398,8 +398,7 @@ inline cudaError_t launch_scan_tq(const CUtensorMap& tmX, const CUtensorMap& tmQ
   switch (TQ) {
     case 1: return launch_scan_inst<KIND, T, 1>(tmX, tmQ, a, smem, st);
     case 4: return launch_scan_inst<KIND, T, 4>(tmX, tmQ, a, smem, st);
-    case 8:
-      if constexpr (KIND != K_MULTI) return launch_scan_inst<KIND, T, 8>(tmX, tmQ, a, smem, st);
+    case 8: return launch_scan_inst<KIND, T, 8>(tmX, tmQ, a, smem, st);
     default: return cudaErrorInvalidValue;
   }
 }
