@@ -66,6 +66,7 @@ struct Args {
   uint64_t* partial;     // [nq][P][kp]
   uint32_t* thr_g;       // [num_qtiles*128] best published k'-th rank value per query (ordered bits), 0xffffffff = none
   unsigned long long* dbg;   // optional [gridDim.x][16] cycle counters (B200IR_GEMM_DEBUG=1), else nullptr
+  int opt;               // experiment switches (B200IR_GEMM_OPT): bit 0 = L2 prefetch of the tile two ahead
 };
 
 #define DBG_T0() (a.dbg ? clock64() : 0ll)
@@ -99,6 +100,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -306,6 +311,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             DBG_ADD(0, t0);
             mbar_expect_tx(B_FULL(s), B_STAGE_BYTES);
             tma_load_2d(smem_u32(sB + s * B_STAGE_BYTES), &tmB, B_FULL(s), kb * BK, t * BN);
+            // pull the same k-block of the tile two ahead into L2 (the shared-memory ring is only 3 k-blocks deep)
+            if ((a.opt & 1) && t + 2 < tile1) tma_prefetch_l2_2d(&tmB, kb * BK, (t + 2) * BN);
           }
           // per-column scale of this tile: its buffer is free once the epilogue released accumulator `buf`
           // two tiles ago (already true by now in steady state: the MMAs of this tile are running)
@@ -782,6 +789,8 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
   a.partial = reinterpret_cast<uint64_t*>(ws + pl.off_partial);
   a.thr_g = reinterpret_cast<uint32_t*>(ws + pl.off_thr);
   static const bool dbg_on = getenv("B200IR_GEMM_DEBUG") != nullptr;
+  static const int opt_flags = getenv("B200IR_GEMM_OPT") ? atoi(getenv("B200IR_GEMM_OPT")) : 0;
+  a.opt = opt_flags;
   static unsigned long long* dbg_buf = nullptr;
   if (dbg_on) {
     if (!dbg_buf) cudaMalloc(&dbg_buf, size_t(kNumSMs) * 16 * 8);
