@@ -42,9 +42,9 @@ constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int SMEM_A = MAX_KB * A_KB_BYTES;  // 128 KB
 constexpr int SMEM_B = B_STAGES * B_STAGE_BYTES;   // 96 KB
 constexpr int SMEM_SCALE = 2 * BN * 4;       // double-buffered per-column scale (rnorm / sqnorm)
-constexpr int SMEM_BARS = 128;
+constexpr int SMEM_BARS = 192;
 constexpr int SMEM_CNT = 2 * BM * 2;        // per-query 16-bit candidate counters: front (warp 0 of the quarter) and back (warp 1)
-constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS + SMEM_CNT;   // 232,064 B <= 232,448
+constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS + SMEM_CNT;   // 232,128 B <= 232,448
 constexpr int THREADS = 384;           // 4 control warps + 8 epilogue warps (two per TMEM lane quarter)
 constexpr int TMEM_COLS = 512;
 
@@ -56,6 +56,7 @@ struct Args {
   int D;
   int num_kb;
   int num_qtiles;
+  int num_qgroups;       // query tiles grouped per cluster (1 per CTA): ceil(num_qtiles / cluster size)
   int P;                 // database partitions
   int tiles_per_part;
   int total_tiles;
@@ -101,6 +102,40 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
 }
+// 2-CTA (cta_group::2) variants: the transaction bytes are signalled on the barrier of the LEADER CTA (rank 0 of the
+// pair: peer bit of the shared::cluster address cleared), MMAs are issued by the leader for both SMs, and commits
+// arrive on the same barrier offset in both CTAs.
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
@@ -143,6 +178,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4,6)=1, A bf16 [7,10)=1, B bf16 [10,13)=1,
 // A/B K-major (bits 15,16 = 0), N>>3 in [17,23), M>>4 in [24,29).
 constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+constexpr uint32_t kInstrDesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t((2 * BM) >> 4) << 24);   // M = 256 across the CTA pair
 
 // ------------------------------------------------------------------------------------ epilogue helpers
 // Warp-cooperative compaction of the candidate lists of the lanes in `mask`: sort, keep the best kp.
@@ -243,24 +279,35 @@ __device__ __forceinline__ float score_of(float dot, float s) {
 }
 
 // ------------------------------------------------------------------------------------ main kernel
-template <int MODE>
+template <int MODE, int NCTA>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
+  // NCTA == 2: the CTA pair of a cluster works on two query tiles and shares every database tile: each CTA stages
+  // HALF of the tile's rows (16 KB per k-block instead of 32 KB, so the ring is 6 deep), the leader issues
+  // tcgen05.mma.cta_group::2 (M = 256 across the pair) and each SM's tensor core reads both halves: shared-memory
+  // traffic per FLOP drops by a third, which is what bounds the 1-CTA kernel.
+  constexpr int NST = NCTA == 2 ? 2 * B_STAGES : B_STAGES;          // ring depth
+  constexpr int STAGE_BYTES = B_STAGE_BYTES / NCTA;                  // bytes of one k-block staged per CTA
+  constexpr int BN_CTA = BN / NCTA;                                  // database rows staged per CTA
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + SMEM_A;
   float* sScale = reinterpret_cast<float*>(smem + SMEM_A + SMEM_B);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_A + SMEM_B + SMEM_SCALE);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 10);
   unsigned short* cnt_s = reinterpret_cast<unsigned short*>(smem + SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS);
 
   const uint32_t bar0 = smem_u32(bars);
   auto B_FULL = [&](int s) { return bar0 + 8u * s; };
-  auto B_EMPTY = [&](int s) { return bar0 + 8u * (3 + s); };
-  const uint32_t A_FULL = bar0 + 8u * 6, A_EMPTY = bar0 + 8u * 7;
-  auto T_FULL = [&](int b) { return bar0 + 8u * (8 + b); };
-  auto T_EMPTY = [&](int b) { return bar0 + 8u * (10 + b); };
-  auto S_FULL = [&](int b) { return bar0 + 8u * (12 + b); };
+  auto B_EMPTY = [&](int s) { return bar0 + 8u * (NST + s); };
+  const uint32_t A_FULL = bar0 + 8u * (2 * NST), A_EMPTY = bar0 + 8u * (2 * NST + 1);
+  auto T_FULL = [&](int b) { return bar0 + 8u * (2 * NST + 2 + b); };
+  auto T_EMPTY = [&](int b) { return bar0 + 8u * (2 * NST + 4 + b); };     // local: this CTA's epilogue released buffer b
+  auto S_FULL = [&](int b) { return bar0 + 8u * (2 * NST + 6 + b); };
+  auto TE_MMA = [&](int b) { return bar0 + 8u * (2 * NST + 8 + b); };      // leader: every epilogue warp of the cluster released b
+  static_assert((2 * NST + 10) * 8 + 8 <= SMEM_BARS, "barrier area");
+  const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / NCTA, nclusters = gridDim.x / NCTA;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -272,45 +319,57 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < B_STAGES; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
     mbar_init(A_FULL, 1);
     mbar_init(A_EMPTY, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(T_FULL(b), 1); mbar_init(T_EMPTY(b), 8); mbar_init(S_FULL(b), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(T_FULL(b), 1); mbar_init(T_EMPTY(b), 8); mbar_init(S_FULL(b), 1); mbar_init(TE_MMA(b), 8 * NCTA);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (NCTA == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();       // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_units = a.num_qtiles * a.P;
+  const int num_units = a.num_qgroups * a.P;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       uint32_t kiter = 0, uiter = 0, titer = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uiter) {
-        const int qt = unit % a.num_qtiles, p = unit / a.num_qtiles;
+      for (int unit = cluster_id; unit < num_units; unit += nclusters, ++uiter) {
+        const int qt = (unit % a.num_qgroups) * NCTA + int(rank), p = unit / a.num_qgroups;
         long long t0 = DBG_T0();
         mbar_wait(A_EMPTY, (uiter & 1) ^ 1);                   // previous unit's MMAs are done with A
         DBG_ADD(1, t0);
-        mbar_expect_tx(A_FULL, uint32_t(a.num_kb) * A_KB_BYTES);
-        for (int kb = 0; kb < a.num_kb; ++kb) tma_load_2d(smem_u32(sA + kb * A_KB_BYTES), &tmA, A_FULL, kb * BK, qt * BM);
+        if (rank == 0) mbar_expect_tx(A_FULL, uint32_t(NCTA) * uint32_t(a.num_kb) * A_KB_BYTES);
+        for (int kb = 0; kb < a.num_kb; ++kb) {
+          if constexpr (NCTA == 2) tma_load_2d_2cta(smem_u32(sA + kb * A_KB_BYTES), &tmA, A_FULL, kb * BK, qt * BM);
+          else tma_load_2d(smem_u32(sA + kb * A_KB_BYTES), &tmA, A_FULL, kb * BK, qt * BM);
+        }
         const int tile0 = p * a.tiles_per_part;
         const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
         for (int t = tile0; t < tile1; ++t, ++titer) {
           for (int kb = 0; kb < a.num_kb; ++kb, ++kiter) {
-            const int s = kiter % B_STAGES;
-            const uint32_t ph = (kiter / B_STAGES) & 1;
+            const int s = kiter % NST;
+            const uint32_t ph = (kiter / NST) & 1;
             t0 = DBG_T0();
             mbar_wait(B_EMPTY(s), ph ^ 1);
             DBG_ADD(0, t0);
-            mbar_expect_tx(B_FULL(s), B_STAGE_BYTES);
-            tma_load_2d(smem_u32(sB + s * B_STAGE_BYTES), &tmB, B_FULL(s), kb * BK, t * BN);
+            if (rank == 0) mbar_expect_tx(B_FULL(s), B_STAGE_BYTES);                  // both halves land on the leader's barrier
+            if constexpr (NCTA == 2) tma_load_2d_2cta(smem_u32(sB + s * STAGE_BYTES), &tmB, B_FULL(s), kb * BK, t * BN + int(rank) * BN_CTA);
+            else tma_load_2d(smem_u32(sB + s * STAGE_BYTES), &tmB, B_FULL(s), kb * BK, t * BN);
             // pull the same k-block of the tile two ahead into L2 (the shared-memory ring is only 3 k-blocks deep)
             if ((a.opt & 1) && t + 2 < tile1) tma_prefetch_l2_2d(&tmB, kb * BK, (t + 2) * BN);
           }
@@ -326,11 +385,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    if (lane == 0 && rank == 0) {
+      // ===================== MMA issuer (leader CTA only) =====================
       uint32_t kiter = 0, titer = 0, uiter = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uiter) {
-        const int p = unit / a.num_qtiles;
+      for (int unit = cluster_id; unit < num_units; unit += nclusters, ++uiter) {
+        const int p = unit / a.num_qgroups;
         const int tile0 = p * a.tiles_per_part;
         const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
         long long t0 = DBG_T0();
@@ -340,29 +399,33 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int t = tile0; t < tile1; ++t, ++titer) {
           const int buf = titer & 1;
           t0 = DBG_T0();
-          mbar_wait(T_EMPTY(buf), ((titer >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+          mbar_wait(TE_MMA(buf), ((titer >> 1) & 1) ^ 1);      // every epilogue warp of the cluster drained this accumulator
           DBG_ADD(4, t0);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + uint32_t(buf * BN);
           for (int kb = 0; kb < a.num_kb; ++kb, ++kiter) {
-            const int s = kiter % B_STAGES;
-            const uint32_t ph = (kiter / B_STAGES) & 1;
+            const int s = kiter % NST;
+            const uint32_t ph = (kiter / NST) & 1;
             t0 = DBG_T0();
             mbar_wait(B_FULL(s), ph);
             DBG_ADD(3, t0);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(sA + kb * A_KB_BYTES);
-            const uint32_t b_addr = smem_u32(sB + s * B_STAGE_BYTES);
+            const uint32_t b_addr = smem_u32(sB + s * STAGE_BYTES);
 #pragma unroll
             for (int k4 = 0; k4 < BK / UMMA_K; ++k4) {
-              tc_mma_bf16(tmem_d, make_smem_desc(a_addr + k4 * UMMA_K * 2), make_smem_desc(b_addr + k4 * UMMA_K * 2),
-                          kInstrDesc, (kb | k4) != 0 ? 1u : 0u);
+              if constexpr (NCTA == 2)
+                tc_mma_bf16_2cta(tmem_d, make_smem_desc(a_addr + k4 * UMMA_K * 2), make_smem_desc(b_addr + k4 * UMMA_K * 2),
+                                 kInstrDesc2, (kb | k4) != 0 ? 1u : 0u);
+              else
+                tc_mma_bf16(tmem_d, make_smem_desc(a_addr + k4 * UMMA_K * 2), make_smem_desc(b_addr + k4 * UMMA_K * 2),
+                            kInstrDesc, (kb | k4) != 0 ? 1u : 0u);
             }
-            tc_commit(B_EMPTY(s));                              // stage reusable once these MMAs retire
+            if constexpr (NCTA == 2) tc_commit_2cta(B_EMPTY(s)); else tc_commit(B_EMPTY(s));   // stage reusable once these MMAs retire
           }
-          tc_commit(T_FULL(buf));                               // accumulator complete -> epilogue
+          if constexpr (NCTA == 2) tc_commit_2cta(T_FULL(buf)); else tc_commit(T_FULL(buf));    // accumulator complete -> epilogue
         }
-        tc_commit(A_EMPTY);
+        if constexpr (NCTA == 2) tc_commit_2cta(A_EMPTY); else tc_commit(A_EMPTY);
       }
     }
   } else if (warp >= 4) {
@@ -413,8 +476,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     };
     uint32_t titer = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-      const int qt = unit % a.num_qtiles, p = unit / a.num_qtiles;
+    for (int unit = cluster_id; unit < num_units; unit += nclusters) {
+      const int qt = (unit % a.num_qgroups) * NCTA + int(rank), p = unit / a.num_qgroups;
       const int q = qt * BM + row;
       thr = q < a.nq ? -INFINITY : INFINITY;                   // padding rows of the last query tile accept nothing
       cnt = 0;                                                 // my end of the list (register; published at every barrier)
@@ -489,7 +552,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(T_EMPTY(buf));
+        if (lane == 0) {
+          mbar_arrive(T_EMPTY(buf));                               // my CTA's scale buffer / accumulator slot is free
+          if (NCTA == 2 && rank != 0) mbar_arrive_remote(TE_MMA(buf), 0);
+          else mbar_arrive(TE_MMA(buf));                           // the leader's MMA issuer may overwrite the accumulator
+        }
         if (dbg_me) {
           a.dbg[blockIdx.x * 16 + 8] += (unsigned long long)(clock64() - t0 - tcomp);
           a.dbg[blockIdx.x * 16 + 9] += (unsigned long long)tcomp;
@@ -514,9 +581,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();       // nobody exits while the peer may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (NCTA == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -689,7 +760,7 @@ static bool encode_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, i
 }
 
 struct Plan {
-  int num_qtiles, total_tiles, P, tiles_per_part, kp, cap, grid, num_kb;
+  int num_qtiles, num_qgroups, ncta, total_tiles, P, tiles_per_part, kp, cap, grid, num_kb;
   size_t off_scale, off_thr, off_cand, off_partial, total_bytes;
 };
 
@@ -703,10 +774,19 @@ static int num_sms() {
   return n;
 }
 
+// cluster size of the main kernel: 2 (tcgen05 cta_group::2) unless B200IR_GEMM_NCTA=1
+static int gemm_ncta() {
+  static const int n = (getenv("B200IR_GEMM_NCTA") && atoi(getenv("B200IR_GEMM_NCTA")) == 1) ? 1 : 2;
+  return n;
+}
+
 static Plan make_plan(int64_t nq, int64_t N, int D, int k, int flags, int sms) {
   Plan pl{};
+  pl.ncta = gemm_ncta();
   pl.num_kb = (D + BK - 1) / BK;
   pl.num_qtiles = int(ceil_div64(nq, BM));
+  pl.num_qgroups = (pl.num_qtiles + pl.ncta - 1) / pl.ncta;
+  const int nclusters_max = sms / pl.ncta;
   pl.total_tiles = int(ceil_div64(N, BN));
   const bool rerank = !(flags & B200IR_FLAG_NO_RERANK);
   pl.cap = 512;
@@ -722,18 +802,18 @@ static Plan make_plan(int64_t nq, int64_t N, int D, int k, int flags, int sms) {
   for (int P = 1; P <= maxP; ++P) {
     const int tpp = (pl.total_tiles + P - 1) / P;
     const int Pe = (pl.total_tiles + tpp - 1) / tpp;
-    const int64_t units = int64_t(pl.num_qtiles) * Pe;
-    const int64_t rounds = ceil_div64(units, sms);
+    const int64_t units = int64_t(pl.num_qgroups) * Pe;
+    const int64_t rounds = ceil_div64(units, nclusters_max);
     const int64_t cost = rounds * (tpp + 3);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; bestP = P; }
   }
   pl.tiles_per_part = (pl.total_tiles + bestP - 1) / bestP;
   pl.P = (pl.total_tiles + pl.tiles_per_part - 1) / pl.tiles_per_part;
-  const int64_t units = int64_t(pl.num_qtiles) * pl.P;
-  pl.grid = int(units < sms ? units : sms);
+  const int64_t units = int64_t(pl.num_qgroups) * pl.P;
+  pl.grid = int(units < nclusters_max ? units : nclusters_max) * pl.ncta;
   size_t off = 0;
   pl.off_scale = off; off += round_up64(size_t(pl.total_tiles) * BN * 4, 256);
-  pl.off_thr = off; off += round_up64(size_t(pl.num_qtiles) * BM * 4, 256);
+  pl.off_thr = off; off += round_up64(size_t(pl.num_qgroups) * pl.ncta * BM * 4, 256);
   pl.off_cand = off; off += round_up64(size_t(pl.grid) * BM * pl.cap * 8, 256);
   pl.off_partial = off; off += round_up64(size_t(nq) * pl.P * pl.kp * 8, 256);
   pl.total_bytes = off;
@@ -769,20 +849,20 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
   const int mode = metric == B200IR_L2 ? MODE_L2 : ((flags & B200IR_FLAG_ABS_SCORE) ? MODE_ABSCOS : MODE_COS);
 
   CUtensorMap tmA, tmB;
-  if (!encode_bf16_rows(&tmA, Q, nq, D, BM) || !encode_bf16_rows(&tmB, X, N, D, BN)) return B200IR_E_DEVICE;
+  if (!encode_bf16_rows(&tmA, Q, nq, D, BM) || !encode_bf16_rows(&tmB, X, N, D, BN / pl.ncta)) return B200IR_E_DEVICE;
 
   float* scale = reinterpret_cast<float*>(ws + pl.off_scale);
   {
     ProfileScope ps(PT_PREP, st);
     const int64_t N_pad = int64_t(pl.total_tiles) * BN;
     row_scale_kernel<<<unsigned(ceil_div64(N_pad, 8)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(X), N, N_pad, D, mode == MODE_L2 ? 1 : 0, scale);
-    cudaError_t em = cudaMemsetAsync(ws + pl.off_thr, 0xff, size_t(pl.num_qtiles) * BM * 4, st);
+    cudaError_t em = cudaMemsetAsync(ws + pl.off_thr, 0xff, size_t(pl.num_qgroups) * pl.ncta * BM * 4, st);
     if (em != cudaSuccess) return int(em);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return int(e);
   }
   Args a{};
-  a.nq = int(nq); a.N = N; a.D = D; a.num_kb = pl.num_kb; a.num_qtiles = pl.num_qtiles; a.P = pl.P;
+  a.nq = int(nq); a.N = N; a.D = D; a.num_kb = pl.num_kb; a.num_qtiles = pl.num_qtiles; a.num_qgroups = pl.num_qgroups; a.P = pl.P;
   a.tiles_per_part = pl.tiles_per_part; a.total_tiles = pl.total_tiles; a.kp = pl.kp; a.cap = pl.cap;
   a.colscale = scale;
   a.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
@@ -800,15 +880,31 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
   {
     ProfileScope ps(PT_GEMM, st);
     cudaError_t e;
-    if (mode == MODE_COS) {
-      e = cudaFuncSetAttribute(gemm_topk_kernel<MODE_COS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-      if (e == cudaSuccess) gemm_topk_kernel<MODE_COS><<<pl.grid, THREADS, SMEM_TOTAL, st>>>(tmA, tmB, a);
-    } else if (mode == MODE_ABSCOS) {
-      e = cudaFuncSetAttribute(gemm_topk_kernel<MODE_ABSCOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-      if (e == cudaSuccess) gemm_topk_kernel<MODE_ABSCOS><<<pl.grid, THREADS, SMEM_TOTAL, st>>>(tmA, tmB, a);
+    auto launch = [&](auto kern, int ncta) -> cudaError_t {
+      cudaError_t le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+      if (le != cudaSuccess) return le;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(unsigned(pl.grid));
+      cfg.blockDim = dim3(THREADS);
+      cfg.dynamicSmemBytes = SMEM_TOTAL;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = unsigned(ncta);
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a);
+    };
+    if (pl.ncta == 2) {
+      if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 2>, 2);
+      else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 2>, 2);
+      else e = launch(gemm_topk_kernel<MODE_L2, 2>, 2);
     } else {
-      e = cudaFuncSetAttribute(gemm_topk_kernel<MODE_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-      if (e == cudaSuccess) gemm_topk_kernel<MODE_L2><<<pl.grid, THREADS, SMEM_TOTAL, st>>>(tmA, tmB, a);
+      if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 1>, 1);
+      else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 1>, 1);
+      else e = launch(gemm_topk_kernel<MODE_L2, 1>, 1);
     }
     if (e != cudaSuccess) return int(e);
     e = cudaGetLastError();
@@ -821,7 +917,7 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
     static const char* names[16] = {"prod_wait_Bempty", "prod_wait_Aempty", "prod_wait_Tempty", "mma_wait_Bfull", "mma_wait_Tempty",
                                     "mma_wait_Afull", "-", "epi_wait_full", "epi_elements", "epi_compact", "epi_unit_end", "-",
                                     "epi_compactions(w0)", "epi_tiles", "-", "-"};
-    fprintf(stderr, "[b200ir gemm debug] grid=%d P=%d tiles/part=%d kp=%d cap=%d (mean cycles per CTA)\n", pl.grid, pl.P, pl.tiles_per_part, pl.kp, pl.cap);
+    fprintf(stderr, "[b200ir gemm debug] grid=%d ncta=%d P=%d tiles/part=%d kp=%d cap=%d (mean cycles per CTA)\n", pl.grid, pl.ncta, pl.P, pl.tiles_per_part, pl.kp, pl.cap);
     for (int sidx = 0; sidx < 16; ++sidx) {
       if (names[sidx][0] == '-') continue;
       double sum = 0, mx = 0;
