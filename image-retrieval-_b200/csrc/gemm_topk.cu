@@ -412,6 +412,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after();
             const uint32_t a_addr = smem_u32(sA + kb * A_KB_BYTES);
             const uint32_t b_addr = smem_u32(sB + s * STAGE_BYTES);
+            t0 = DBG_T0();
 #pragma unroll
             for (int k4 = 0; k4 < BK / UMMA_K; ++k4) {
               if constexpr (NCTA == 2)
@@ -422,6 +423,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             kInstrDesc, (kb | k4) != 0 ? 1u : 0u);
             }
             if constexpr (NCTA == 2) tc_commit_2cta(B_EMPTY(s)); else tc_commit(B_EMPTY(s));   // stage reusable once these MMAs retire
+            DBG_ADD(6, t0);
           }
           if constexpr (NCTA == 2) tc_commit_2cta(T_FULL(buf)); else tc_commit(T_FULL(buf));    // accumulator complete -> epilogue
         }
@@ -915,7 +917,7 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
     cudaStreamSynchronize(st);
     cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
     static const char* names[16] = {"prod_wait_Bempty", "prod_wait_Aempty", "prod_wait_Tempty", "mma_wait_Bfull", "mma_wait_Tempty",
-                                    "mma_wait_Afull", "-", "epi_wait_full", "epi_elements", "epi_compact", "epi_unit_end", "-",
+                                    "mma_wait_Afull", "mma_issue", "epi_wait_full", "epi_elements", "epi_compact", "epi_unit_end", "-",
                                     "epi_compactions(w0)", "epi_tiles", "-", "-"};
     fprintf(stderr, "[b200ir gemm debug] grid=%d ncta=%d P=%d tiles/part=%d kp=%d cap=%d (mean cycles per CTA)\n", pl.grid, pl.ncta, pl.P, pl.tiles_per_part, pl.kp, pl.cap);
     for (int sidx = 0; sidx < 16; ++sidx) {
