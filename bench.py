@@ -124,6 +124,23 @@ def make_unit_rows(torch, n, d, seed, device, dtype, chunk=250_000):
     return out
 
 
+def init_nccl(torch, dist, dev):
+    """init_process_group + first collective with stdout pointed at stderr: NCCL prints its version banner on stdout
+    when NCCL_DEBUG >= VERSION, and stdout must carry exactly one JSON line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        t = torch.zeros(1, device=dev)
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -238,9 +255,7 @@ def run_headline(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (no NCCL version banner)
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(torch, dist, dev)
     lib = _lib.load()
     ops.device()
 
@@ -499,7 +514,7 @@ def run_config4(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(torch, dist, dev)
     total = args.rows or 10_000_000
     b, e = shard_range(total, world, rank)
     n_local = e - b
