@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(128) finalize_topk_kernel(const uint64_t* __re
   emit_topk<E>(r, lane, k, mp, index_offset, out_score, out_idx, int64_t(q));
 }
 
-// Cross-shard merge: score/idx [R, nq, k] -> [nq, k] ordered by (score, global idx).
+// Cross-shard merge: score/idx lists of R shards -> [nq, k] ordered by (score, global idx).
+// Every shard list is sorted, so the best of the shards' k-th scores bounds the global k-th score: entries worse than
+// it are dropped while streaming (ties kept), and what survives (about k..2k keys) usually fits one sort round.
 template <int E>
 __global__ void __launch_bounds__(128) merge_topk_kernel(int descending, const float* __restrict__ score,
                                                         const int64_t* __restrict__ idx, int64_t score_stride,
@@ -83,36 +85,72 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(int descending, const f
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (q >= nq) return;
+  __shared__ key128_t stage_s[4][32 * E];
+  key128_t* stage = stage_s[threadIdx.x >> 5];
   const key128_t kInf = ~key128_t(0);
   const int64_t per_query = int64_t(R) * k;
+  const int64_t qoff = int64_t(q) * k;
+  // Two valid bounds on the global k-th score (ordered domain, smaller = better):
+  //   (a) the best of the shards' k-th scores (that shard alone holds k entries at least as good);
+  //   (b) the worst of the shards' m-th scores, m = ceil(k / R): together the shards hold R*m >= k entries at least
+  //       as good.  For a balanced row-sharded store (b) is the tight one (each shard contributes ~k/R winners).
+  const int m = (k + R - 1) / R;
+  uint32_t bound = 0xffffffffu, bound_b = 0u;
+  bool b_ok = true;
+  for (int sh = lane; sh < R; sh += 32) {
+    if (idx[int64_t(sh) * idx_stride + qoff + k - 1] >= 0) {
+      const float v = score[int64_t(sh) * score_stride + qoff + k - 1];
+      bound = min(bound, f32_to_ordered(descending ? -v : v));
+    }
+    if (idx[int64_t(sh) * idx_stride + qoff + m - 1] >= 0) {
+      const float v = score[int64_t(sh) * score_stride + qoff + m - 1];
+      bound_b = max(bound_b, f32_to_ordered(descending ? -v : v));
+    } else {
+      b_ok = false;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    bound = min(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+    bound_b = max(bound_b, __shfl_xor_sync(0xffffffffu, bound_b, o));
+  }
+  if (__all_sync(0xffffffffu, b_ok)) bound = min(bound, bound_b);
   key128_t r[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) r[e] = kInf;
-  int kept = 0;
-  int64_t pos = 0;
-  do {
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int i = lane * E + e;
-      if (i >= kept) {
-        const int64_t s = pos + (i - kept);
-        key128_t key = kInf;
-        if (s < per_query) {
-          const int shard = int(s / k), j = int(s % k);
-          const int64_t off = int64_t(q) * k + j;
-          const int64_t id = idx[int64_t(shard) * idx_stride + off];
-          if (id >= 0) {
-            const float v = score[int64_t(shard) * score_stride + off];
-            key = (key128_t(f32_to_ordered(descending ? -v : v)) << 64) | key128_t(uint64_t(id));
-          }
-        }
-        r[e] = key;
+  int kept = 0, fill = 0;
+  for (int64_t base = 0; base < per_query; base += 32) {
+    const int64_t s = base + lane;
+    key128_t key = kInf;
+    bool keep = false;
+    if (s < per_query) {
+      const int shard = int(s / k), j = int(s % k);
+      const int64_t id = idx[int64_t(shard) * idx_stride + qoff + j];
+      if (id >= 0) {
+        const float v = score[int64_t(shard) * score_stride + qoff + j];
+        const uint32_t o = f32_to_ordered(descending ? -v : v);
+        keep = o <= bound;
+        key = (key128_t(o) << 64) | key128_t(uint64_t(id));
       }
     }
-    pos += 32 * E - kept;
-    warp_sort<E>(r, lane);
-    kept = k;
-  } while (pos < per_query);
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (keep) stage[fill + __popc(m & ((1u << lane) - 1))] = key;
+    fill += __popc(m);
+    if (fill > 32 * E - kept - 32 || base + 32 >= per_query) {
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = lane * E + e;
+        if (i >= kept) r[e] = (i - kept) < fill ? stage[i - kept] : kInf;
+      }
+      warp_sort<E>(r, lane);
+      kept = min(kept + fill, k);
+      fill = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) if (lane * E + e >= kept) r[e] = kInf;
+      __syncwarp();
+    }
+  }
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int i = lane * E + e;

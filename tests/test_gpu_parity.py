@@ -203,6 +203,43 @@ def test_merge_matches_oracle(ops):
     assert mi.cpu().tolist() == [[10, 3]]
 
 
+@pytest.mark.parametrize("R,k", [(2, 100), (8, 100), (8, 256), (5, 7), (16, 3), (3, 1)])
+def test_merge_unbalanced_and_short_shards(ops, R, k):
+    """The merge's score bound must hold when one shard owns every winner, when shards are shorter than k
+    (padded with idx -1) and when k < R."""
+    import torch
+    rng = np.random.default_rng(100 + R + k)
+    nq = 37
+    for desc in (False, True):
+        for case in ("skewed", "short", "random"):
+            n_r = [k + 50] * R
+            if case == "short":
+                n_r = [int(x) for x in rng.integers(0, k + 1, size=R)]
+                n_r[0] = max(n_r[0], 1)
+            cols = []
+            for r in range(R):
+                a = rng.standard_normal((nq, n_r[r])).astype(np.float32)
+                if case == "skewed" and r == R - 1:
+                    a += -10.0 if not desc else 10.0                   # this shard owns the whole top-k
+                cols.append(a)
+            full = np.concatenate(cols, axis=1)
+            kk = min(k, full.shape[1])
+            fv, fi = OS.topk(full, kk, desc)
+            pv = np.full((R, nq, k), -np.inf if desc else np.inf, np.float32)
+            pi = np.full((R, nq, k), -1, np.int64)
+            off = 0
+            for r in range(R):
+                if n_r[r]:
+                    v, i = OS.topk(cols[r], min(k, n_r[r]), desc)
+                    pv[r, :, :v.shape[1]] = v
+                    pi[r, :, :v.shape[1]] = i + off
+                off += n_r[r]
+            mv, mi = ops.topk_merge(torch.from_numpy(pv).cuda(), torch.from_numpy(pi).cuda(), desc)
+            mv, mi = mv.cpu().numpy(), mi.cpu().numpy()
+            assert np.array_equal(mi[:, :kk], fi) and np.array_equal(mv[:, :kk], fv), (case, desc)
+            assert (mi[:, kk:] == -1).all()
+
+
 def test_sharded_equals_single(ops):
     """Row-sharded search (emulated ranks on one GPU) == single-shard search, exactly."""
     import torch
