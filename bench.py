@@ -476,6 +476,27 @@ def run_side(args):
                              "peak": peak / 1e12, "unit": "T lane-instr/s", "frac": lane_ops / (kms * 1e-3) / peak, "kernel_ms": kms,
                              "note": "CUDA-core bound: 5.25 fp32 lane-instructions per element pair; peak = 148 SMs x 128 lanes x 1.965 GHz"}}
         print(json.dumps(line))
+    elif w == "pairs":
+        # explicit pair lists (mi_analysis.py:256-297): P random pairs over an N x D fp32 store, seven values per pair
+        N = args.rows or 1_000_000
+        D = args.dim or 512
+        P = args.queries or 4_000_000
+        g = torch.Generator(device=dev); g.manual_seed(5101)
+        X = torch.randn((N, D), generator=g, device=dev)
+        ia = torch.randint(0, N, (P,), generator=g, device=dev)
+        ib = torch.randint(0, N, (P,), generator=g, device=dev)
+        ms, kms, launches, clocks = time_fn(lambda: ops.pair_metrics(X, None, ia, ib), 7)
+        bytes_alg = P * (2 * D * 4 + 16 + 28)
+        ach = bytes_alg / (kms * 1e-3) / 1e9
+        line = {"metric": f"pairs/sec (get_all_metrics over an explicit pair list, {N}x{D} fp32 store)", "value": P / (ms * 1e-3),
+                "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                "higher_is_better": True, "dtype": "f32", "data": "synthetic N(0,1), uniform random pairs",
+                "config": {"workload": f"pairs: {P} pairs over {N}x{D} fp32", "l2_policy": "inputs larger than L2"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "pair_metrics", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                             "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel_ms": kms,
+                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}}
+        print(json.dumps(line))
     elif w == "config1":
         def palette_images(b, seed):
             """a few flat colour blocks + small noise per image: peaky histograms with many exact ties"""

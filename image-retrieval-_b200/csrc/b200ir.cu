@@ -4,6 +4,7 @@
 #include "scan_plan.h"
 #include "select.cuh"
 #include "histogram.cuh"
+#include "pairs.cuh"
 #include "gemm_topk.h"
 #include "profile.h"
 
@@ -259,6 +260,18 @@ int b200ir_allpairs_eval(const float* X, const int32_t* cat, const int32_t* col,
   return int(run_allpairs_eval(X, cat, col, N, D, nbins, lo_host, hi_host, thresholds_host, nthr,
                                reinterpret_cast<unsigned long long*>(hist), reinterpret_cast<unsigned long long*>(thr_counts),
                                static_cast<unsigned char*>(workspace), st));
+}
+
+int b200ir_pair_metrics(int dtype, const void* A, int64_t NA, const void* B, int64_t NB, int D,
+                        const int64_t* ia, const int64_t* ib, int64_t P, float* out, void* stream) {
+  if (!valid_dtype(dtype) || NA < 0 || NB < 0 || D <= 0 || P < 0) return B200IR_E_ARG;
+  if (P == 0) return 0;
+  if (!ia || !ib || !out || (NA > 0 && !A) || (NB > 0 && !B)) return B200IR_E_ARG;
+  if (reinterpret_cast<uintptr_t>(A) % elem_size(dtype) || reinterpret_cast<uintptr_t>(B) % elem_size(dtype)) return B200IR_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope ps(PT_MISC, st);
+  if (dtype == B200IR_F32) return int(launch_pair_metrics<float>(A, NA, B, NB, D, ia, ib, P, out, st));
+  return int(launch_pair_metrics<__nv_bfloat16>(A, NA, B, NB, D, ia, ib, P, out, st));
 }
 
 int b200ir_histogram(int colorspace, const uint8_t* img, int64_t B, int H, int W, int bins_per_channel,

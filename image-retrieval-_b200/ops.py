@@ -232,6 +232,29 @@ def allpairs_eval(X, category, color, ranges, nbins=1024, thresholds=None):
     return hist, thr_counts
 
 
+PAIR_METRICS = ("cosine_similarity", "cosine_distance", "angular_distance", "l1_distance", "l2_distance", "linf_distance",
+                "magnitude_difference")                                       # get_all_metrics key order
+
+
+def pair_metrics(A, B, ia, ib):
+    """get_all_metrics (geometric_metrics.py:114-129) for the listed pairs (A[ia[p]], B[ib[p]]): (7, P) fp32 device
+    tensor in PAIR_METRICS order.  B=None pairs rows of A with each other.  Unknown rows give NaN columns."""
+    A = as_device_matrix(A)
+    B = A if B is None else as_device_matrix(B, dtype=A.dtype)
+    if B.dtype != A.dtype or B.shape[1] != A.shape[1]:
+        raise ValueError("pair_metrics: A and B must share dtype and dimension")
+    ia = torch.as_tensor(ia, dtype=torch.int64).to(A.device).contiguous().view(-1)
+    ib = torch.as_tensor(ib, dtype=torch.int64).to(A.device).contiguous().view(-1)
+    if ia.numel() != ib.numel():
+        raise ValueError("pair_metrics: index lists differ in length")
+    P = ia.numel()
+    out = torch.empty((len(PAIR_METRICS), P), dtype=torch.float32, device=A.device)
+    lib = _lib.load()
+    _lib.check(lib.b200ir_pair_metrics(_dtype_id(A), _ptr(A), A.shape[0], _ptr(B), B.shape[0], A.shape[1], _ptr(ia), _ptr(ib), P,
+                                       _ptr(out), _stream()), "pair_metrics")
+    return out
+
+
 def histogram(images, colorspace="rgb"):
     """(B,H,W,3) uint8 RGB -> (B,512) int32 counts on the device (8x8x8 joint bins)."""
     dev = device()

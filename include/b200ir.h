@@ -144,6 +144,18 @@ int b200ir_allpairs_eval(const float* X, const int32_t* cat, const int32_t* col,
                          uint64_t* hist, uint64_t* thr_counts, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Explicit pair lists: replaces the per-pair get_all_metrics calls of ColorMIAnalyzer.calculate_distances
+ * (mi_analysis.py:256-297 over pairs.json; geometric_metrics.py:114-129).  For p in [0, P): the pair
+ * (A[ia[p]], B[ib[p]]) -> out[m][p], out [7][P] fp32, m in get_all_metrics key order:
+ *   0 cosine_similarity, 1 cosine_distance, 2 angular_distance, 3 l1_distance (/D), 4 l2_distance (/sqrt(D)),
+ *   5 linf_distance, 6 magnitude_difference.  A and B may be the same matrix.  A pair naming a row outside
+ *   [0, NA) x [0, NB) is written as NaN (the reference logs a warning and skips it, :278-280).
+ */
+#define B200IR_PAIR_OUTPUTS 7
+int b200ir_pair_metrics(int dtype, const void* A, int64_t NA, const void* B, int64_t NB, int D,
+                        const int64_t* ia, const int64_t* ib, int64_t P, float* out, void* stream);
+
+/*
  * 512-bin joint colour histogram of uint8 images, img [B, H, W, 3] interleaved RGB,
  * out_counts [B, bins^3] uint32, bin = (c0bin*bins + c1bin)*bins + c2bin with
  * c*bin = c>>5 (H: h*8/180).  bins_per_channel must be 8.  The embedding producer

@@ -66,3 +66,50 @@ def pr_from_counts(thr_counts_metric):
     fp = np.cumsum(c0[:-1])
     fn = c1.sum() - tp
     return np.stack([tp, fp, fn], axis=1)
+
+
+def calculate_distances(embeddings, pairs, metric_names=METRICS, relationship_types=RELATIONSHIP_TYPES):
+    """mi_analysis.py:256-297 restated: distances[metric][rel_type] = list of get_all_metrics values over the listed
+    (path1, path2) pairs, skipping pairs with a missing embedding (:278-280)."""
+    distances = {m: {r: [] for r in relationship_types} for m in metric_names}
+    for rel_type in relationship_types:
+        for p1, p2 in pairs.get(rel_type, []):
+            if p1 not in embeddings or p2 not in embeddings:
+                continue
+            allm = M.get_all_metrics(embeddings[p1], embeddings[p2])
+            for m in metric_names:
+                distances[m][rel_type].append(allm[m])
+    return distances
+
+
+def generate_relationship_pairs(metadata, categories, colors):
+    """imageProcessing.py:296-387 restated (loop structure kept): metadata rows -> four pair lists."""
+    from collections import defaultdict
+    pairs = {r: [] for r in RELATIONSHIP_TYPES}
+    if len(metadata) < 2:
+        return pairs
+    groups = defaultdict(list)
+    for meta in metadata:
+        groups[(meta["category"], meta["color"])].append(meta["path"])
+    for (category, color), paths in list(groups.items()):
+        if len(paths) >= 2:
+            for i in range(len(paths)):
+                for j in range(i + 1, len(paths)):
+                    pairs["same_object_same_color"].append((paths[i], paths[j]))
+    for category in categories:
+        cc = [color for (cat, color), paths in groups.items() if cat == category and paths]
+        if len(cc) >= 2:
+            for i1, c1 in enumerate(cc):
+                for c2 in cc[i1 + 1:]:
+                    for a in groups[(category, c1)]:
+                        for b in groups[(category, c2)]:
+                            pairs["same_object_diff_color"].append((a, b))
+    for color in colors:
+        cats = [cat for (cat, col), paths in groups.items() if col == color and paths]
+        if len(cats) >= 2:
+            for i1, k1 in enumerate(cats):
+                for k2 in cats[i1 + 1:]:
+                    for a in groups[(k1, color)]:
+                        for b in groups[(k2, color)]:
+                            pairs["diff_object_same_color"].append((a, b))
+    return pairs    # diff_object_diff_color iterates a python set (:358-360): its order is unspecified, compared as a set

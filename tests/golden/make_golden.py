@@ -10,6 +10,8 @@ Outputs (committed, small):
   metrics_golden.npz  - vectors + every reference metric, pair by pair
   search_golden.npz   - DB/query vectors + reference top-k paths/scores
   hist_golden.npz     - images + cv2.calcHist counts (RGB, HSV)  [OpenCV, not the reference]
+  pairs_golden.json   - metadata rows -> the reference's generate_relationship_pairs output, and the per-pair
+                        get_all_metrics values of mi_analysis.py:277-291 for seeded embeddings of those paths
 """
 import os
 import sys
@@ -113,7 +115,46 @@ def hist_golden():
                         rgb=np.array(rgb).astype(np.uint32), hsv=np.array(hsv).astype(np.uint32))
 
 
+def pairs_golden():
+    """ColorDatasetManager.generate_relationship_pairs (imageProcessing.py:296-387) run on hand-made metadata, then the
+    calculate_distances loop body (mi_analysis.py:277-291; mi_analysis itself needs matplotlib and cannot be imported)."""
+    import json
+    import tempfile
+    from imageProcessing import ColorDatasetManager
+    rng = np.random.default_rng(77)
+    with tempfile.TemporaryDirectory() as tmp:
+        mgr = ColorDatasetManager(base_dir=os.path.join(tmp, "ds"))
+        base = str(mgr.base_dir)
+        meta = []
+        for category in ("dog", "car", "boat", "chair"):
+            for color in ("brown", "white", "black"):
+                if (category, color) in (("boat", "black"), ("chair", "brown"), ("chair", "white")):
+                    continue                                    # ragged: some cells empty, chair has one colour
+                for i in range(int(rng.integers(1, 4))):
+                    meta.append({"path": os.path.join(base, category, color, f"{i + 1}.jpg"), "category": category, "color": color})
+        mgr.metadata = meta
+        pairs = mgr.generate_relationship_pairs()
+        rel = lambda p: p[len(base) + 1:]
+        paths = [m["path"] for m in meta]
+        emb = {p: rng.standard_normal(64).astype(np.float32) for p in paths}
+        emb[paths[3]] = np.zeros(64, np.float32)
+        dist = {}
+        for rel_type, lst in pairs.items():
+            for n in NAMES:
+                dist.setdefault(n, {})[rel_type] = [float(G.get_all_metrics(emb[a], emb[b])[n]) for a, b in lst]
+        out = {"metadata": [{"path": rel(m["path"]), "category": m["category"], "color": m["color"]} for m in meta],
+               "categories": mgr.categories, "colors": mgr.colors,
+               "pairs": {r: [[rel(a), rel(b)] for a, b in lst] for r, lst in pairs.items()},
+               "embeddings": {rel(p): [float(x) for x in v] for p, v in emb.items()},
+               "distances": dist}
+    with open(os.path.join(HERE, "pairs_golden.json"), "w") as f:
+        json.dump(out, f)
+
+
 if __name__ == "__main__":
+    pairs_golden()
+    if "--pairs-only" in sys.argv:
+        sys.exit(0)
     metrics_golden()
     search_golden()
     hist_golden()

@@ -118,3 +118,57 @@ def test_npz_cache_roundtrip_without_gpu(tmp_path):
     out = tmp_path / "out.npz"
     app.save_embeddings_npz(out)
     assert set(EnhancedImageSearchApp.load_embeddings_npz(out)) == set(app.embeddings)
+
+
+def _pairs_gold(golden_dir):
+    import json
+    with open(os.path.join(golden_dir, "pairs_golden.json")) as f:
+        return json.load(f)
+
+
+def test_relationship_pairs_match_reference_run(golden_dir):
+    """generate_relationship_pairs (imageProcessing.py:296-387): product + oracle restatement vs the reference's own
+    output (tests/golden/make_golden.py pairs_golden)."""
+    from image_retrieval_b200.mi_eval import generate_relationship_pairs
+    from oracle import evaluation as E
+    g = _pairs_gold(golden_dir)
+    want = {r: [tuple(p) for p in lst] for r, lst in g["pairs"].items()}
+    got = generate_relationship_pairs(g["metadata"], g["categories"], g["colors"])
+    ora = E.generate_relationship_pairs(g["metadata"], g["categories"], g["colors"])
+    for r in ("same_object_same_color", "same_object_diff_color", "diff_object_same_color"):
+        assert got[r] == want[r] and ora[r] == want[r], r
+    # the reference walks a python set of categories here (:358-360): pair order and orientation follow its hash order
+    unordered = lambda lst: sorted(tuple(sorted(p)) for p in lst)
+    assert unordered(got["diff_object_diff_color"]) == unordered(want["diff_object_diff_color"])
+
+
+def test_mi_dataset_files_roundtrip(tmp_path, golden_dir):
+    """metadata.csv + pairs.json + embeddings .npz / .npy as the reference writes them (imageProcessing.py:389-434,
+    app_pipeline.py:34-58) are read back with the reference's messages (mi_analysis.py:199-254)."""
+    import pandas as pd
+    from image_retrieval_b200.mi_eval import ColorMIAnalyzer, save_pairs
+    g = _pairs_gold(golden_dir)
+    base = tmp_path / "color_dataset"
+    an = ColorMIAnalyzer(base_dir=str(base))
+    ok, msg = an.load_dataset(str(tmp_path / "e.npz"))
+    assert not ok and msg.startswith("Metadata file not found")
+    base.mkdir()
+    pd.DataFrame([{**m, "path": str(base / m["path"])} for m in g["metadata"]]).to_csv(base / "metadata.csv", index=False)
+    ok, msg = an.load_dataset(str(tmp_path / "e.npz"))
+    assert not ok and msg.startswith("Pairs file not found")
+    save_pairs(base, {r: [(str(base / a), str(base / b)) for a, b in lst] for r, lst in g["pairs"].items()})
+    import json
+    assert json.load(open(base / "pairs.json")) == g["pairs"]                   # relative paths on disk
+    ok, msg = an.load_dataset(str(tmp_path / "missing.npz"))
+    assert not ok and msg.startswith("Error loading embeddings")
+    emb = {str(base / p): np.asarray(v, np.float32) for p, v in g["embeddings"].items()}
+    np.savez(tmp_path / "bad.npz", other=np.zeros(3))
+    ok, msg = an.load_dataset(str(tmp_path / "bad.npz"))
+    assert not ok and msg.startswith("No 'embeddings' array found")
+    np.savez(tmp_path / "e.npz", embeddings=emb)
+    np.save(tmp_path / "e.npy", emb, allow_pickle=True)
+    for f in ("e.npz", "e.npy"):
+        ok, msg = an.load_dataset(str(tmp_path / f))
+        assert ok and msg == "Dataset loaded successfully"
+        assert set(an.embeddings) == set(emb) and len(an.metadata) == len(g["metadata"])
+        assert an.pairs["same_object_diff_color"][0] == tuple(str(base / p) for p in g["pairs"]["same_object_diff_color"][0])

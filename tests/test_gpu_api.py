@@ -135,3 +135,38 @@ def test_allpairs_evaluator_surface():
     assert np.abs(prec - want_p).max() < 0.02 and np.abs(rec - want_r).max() < 0.02
     d = ev.densities()
     assert set(d) == set(METRIC_NAMES) and set(d["l1_distance"]) == set(RELATIONSHIP_TYPES)
+
+
+def test_color_mi_analyzer_distances_match_reference_run(tmp_path, golden_dir):
+    """ColorMIAnalyzer.load_dataset + calculate_distances (mi_analysis.py:199-297) on the reference's file formats ==
+    the values the reference's get_all_metrics produced for the same pair lists (tests/golden/pairs_golden.json)."""
+    import json
+    import pandas as pd
+    from image_retrieval_b200.mi_eval import ColorMIAnalyzer, save_pairs
+    with open(os.path.join(golden_dir, "pairs_golden.json")) as f:
+        g = json.load(f)
+    base = tmp_path / "color_dataset"
+    base.mkdir()
+    pd.DataFrame([{**m, "path": str(base / m["path"])} for m in g["metadata"]]).to_csv(base / "metadata.csv", index=False)
+    pairs = {r: [(str(base / a), str(base / b)) for a, b in lst] for r, lst in g["pairs"].items()}
+    pairs["same_object_same_color"].insert(1, (str(base / "nowhere.jpg"), pairs["same_object_same_color"][0][0]))   # skipped
+    save_pairs(base, pairs)
+    np.savez(tmp_path / "e.npz", embeddings={str(base / p): np.asarray(v, np.float32) for p, v in g["embeddings"].items()})
+    an = ColorMIAnalyzer(base_dir=str(base))
+    assert an.load_dataset(str(tmp_path / "e.npz")) == (True, "Dataset loaded successfully")
+    an.calculate_distances()
+    assert list(an.distances) == an.metric_names
+    for m in an.metric_names:
+        for r in an.relationship_types:
+            want = np.asarray(g["distances"][m][r], np.float64)
+            got = np.asarray(an.distances[m][r], np.float64)
+            assert got.shape == want.shape, (m, r)
+            assert np.all(np.abs(got - want) <= 1e-5 * np.abs(want) + 2e-6), (m, r)
+    thr, prec, rec = an.precision_recall("cosine_distance")
+    from oracle import evaluation as E
+    d = g["distances"]["cosine_distance"]
+    ref = E.pr_curve_reference(d["same_object_diff_color"] + d["same_object_same_color"],
+                               [1] * len(d["same_object_diff_color"]) + [0] * len(d["same_object_same_color"]), thr)
+    tp, fp, fn = ref[:, 0], ref[:, 1], ref[:, 2]
+    assert np.allclose(prec, np.where(tp + fp > 0, tp / np.maximum(tp + fp, 1), 0.0), atol=0.05)
+    assert np.allclose(rec, np.where(tp + fn > 0, tp / np.maximum(tp + fn, 1), 0.0), atol=0.05)

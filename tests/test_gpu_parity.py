@@ -480,3 +480,37 @@ def test_allpairs_eval_counts(ops):
     # relationship-type totals
     for t in range(4):
         assert hist[0, t].sum() == int((r == t).sum())
+
+
+# ------------------------------------------------------------------------------- explicit pair lists
+@pytest.mark.parametrize("D,dtype", [(512, "f32"), (64, "f32"), (7, "f32"), (513, "f32"), (512, "bf16"), (36, "bf16")])
+def test_pair_metrics_match_oracle(ops, D, dtype):
+    """b200ir_pair_metrics == get_all_metrics pair by pair (geometric_metrics.py:114-129), incl. a zero row,
+    a self pair and rows named outside the store (NaN column)."""
+    import torch
+    rng = np.random.default_rng(D)
+    A = synth.gaussian(300, D, 61)
+    B = synth.gaussian(200, D, 62)
+    A[5] = 0.0
+    B[9] = A[17]
+    if dtype == "bf16":
+        A, B = OM.bf16_round(A), OM.bf16_round(B)
+    P = 1000
+    ia = rng.integers(0, 300, size=P); ib = rng.integers(0, 200, size=P)
+    ia[:3] = (5, 17, 5); ib[:3] = (0, 9, 9)
+    ia[10], ib[11] = 300, -1                                     # unknown rows
+    tA = torch.from_numpy(A).bfloat16() if dtype == "bf16" else A
+    tB = torch.from_numpy(B).bfloat16() if dtype == "bf16" else B
+    got = ops.pair_metrics(tA, tB, ia, ib).cpu().numpy()
+    assert got.shape == (7, P) and np.isnan(got[:, 10]).all() and np.isnan(got[:, 11]).all()
+    for p in [q for q in range(P) if q not in (10, 11)]:
+        want = OM.get_all_metrics(A[ia[p]], B[ib[p]])
+        for mi, name in enumerate(ops.PAIR_METRICS):
+            # absolute floors: cosine family 2e-6, arccos amplification near 0 / pi, |a|-|b| is a difference of ~sqrt(D) norms
+            tol = {"cosine_similarity": 2e-6, "cosine_distance": 2e-6, "angular_distance": 2e-3, "magnitude_difference": 1e-5}.get(name, 1e-6)
+            assert abs(got[mi, p] - float(want[name])) <= 1e-5 * abs(float(want[name])) + tol, (p, name, got[mi, p], want[name])
+    assert got[0, 0] == 0.0 and got[1, 0] == 1.0 and abs(got[2, 0] - np.pi / 2) < 1e-6       # zero vector (:16-17)
+    assert got[5, 1] == 0.0 and got[3, 1] == 0.0                                             # identical rows
+    same = ops.pair_metrics(tA, None, [1, 2], [2, 1]).cpu().numpy()                          # symmetric within one store
+    assert np.array_equal(same[:, 0], same[:, 1])
+    assert ops.pair_metrics(tA, None, [], []).shape == (7, 0)

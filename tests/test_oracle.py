@@ -171,3 +171,18 @@ def test_evaluation_oracle_matches_reference_pr_loop(gold):
     ref = M.get_all_metrics(X[i], X[j])
     for m in E.METRICS:
         np.testing.assert_allclose(vals[m][i, j], ref[m], rtol=2e-5, atol=2e-6)
+
+
+def test_pair_list_distances_match_reference_run(golden_dir):
+    """calculate_distances restatement (mi_analysis.py:256-297) vs values produced by the reference's get_all_metrics."""
+    import json
+    from oracle import evaluation as E
+    with open(os.path.join(golden_dir, "pairs_golden.json")) as f:
+        g = json.load(f)
+    emb = {p: np.asarray(v, np.float32) for p, v in g["embeddings"].items()}
+    pairs = {r: [tuple(p) for p in lst] for r, lst in g["pairs"].items()}
+    pairs["same_object_same_color"].append(("not/in/store.jpg", g["metadata"][0]["path"]))   # skipped (:278-280)
+    d = E.calculate_distances(emb, pairs)
+    for m in E.METRICS:
+        for r in E.RELATIONSHIP_TYPES:
+            assert [float(x) for x in d[m][r]] == g["distances"][m][r], (m, r)
