@@ -476,6 +476,28 @@ def run_side(args):
                              "peak": peak / 1e12, "unit": "T lane-instr/s", "frac": lane_ops / (kms * 1e-3) / peak, "kernel_ms": kms,
                              "note": "CUDA-core bound: 5.25 fp32 lane-instructions per element pair; peak = 148 SMs x 128 lanes x 1.965 GHz"}}
         print(json.dumps(line))
+    elif w == "resize":
+        # image front-end: PIL-exact bicubic resize (shorter edge -> 224) + centre crop, then the 512-bin histogram
+        B = args.rows or 2048
+        H, W = 480, 640
+        g = torch.Generator(device=dev); g.manual_seed(1003)
+        imgs = torch.randint(0, 256, (B, H, W, 3), generator=g, device=dev, dtype=torch.uint8)
+        ms, kms, launches, clocks = time_fn(lambda: ops.histogram(ops.resize_crop(imgs, 224)), 8)
+        rh, rw = ops.shortest_edge_size(H, W, 224)
+        scale = W / rw
+        left = (rw - 224) // 2
+        cols = min(W, int((left + 224) * scale + 2 * scale + 1)) - max(0, int(left * scale - 2 * scale))
+        bytes_alg = B * (H * cols * 3 + 224 * 224 * 3)            # source window the crop depends on + cropped output
+        ach = bytes_alg / (kms * 1e-3) / 1e9
+        line = {"metric": f"images/sec (bicubic resize {H}x{W} -> 224 crop + 512-bin histogram)", "value": B / (ms * 1e-3),
+                "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                "higher_is_better": True, "dtype": "u8", "data": "synthetic uniform pixels",
+                "config": {"workload": f"resize: {B} images {H}x{W}x3 -> 224x224x3 -> histogram", "l2_policy": "inputs larger than L2"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "resize_crop", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                             "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel_ms": kms,
+                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}}
+        print(json.dumps(line))
     elif w == "pairs":
         # explicit pair lists (mi_analysis.py:256-297): P random pairs over an N x D fp32 store, seven values per pair
         N = args.rows or 1_000_000

@@ -5,6 +5,7 @@
 #include "select.cuh"
 #include "histogram.cuh"
 #include "pairs.cuh"
+#include "resize.cuh"
 #include "gemm_topk.h"
 #include "profile.h"
 
@@ -302,6 +303,33 @@ int b200ir_histogram(int colorspace, const uint8_t* img, int64_t B, int H, int W
     histogram_kernel<false><<<unsigned(B * slices), kHistThreads, 0, st>>>(img, pixels, slices, vector_ok, out_counts);
   }
   return int(cudaGetLastError());
+}
+
+static bool resize_args_ok(int H, int W, int rh, int rw, int top, int left, int ch, int cw) {
+  return H > 0 && W > 0 && rh > 0 && rw > 0 && ch > 0 && cw > 0 && top >= 0 && left >= 0 && top + ch <= rh && left + cw <= rw &&
+         int64_t(W) * 3 < (int64_t(1) << 30) && int64_t(cw) * 3 < (1 << 20);
+}
+
+size_t b200ir_resize_crop_workspace_bytes(int H, int W, int resized_h, int resized_w, int crop_top, int crop_left,
+                                          int crop_h, int crop_w) {
+  if (!resize_args_ok(H, W, resized_h, resized_w, crop_top, crop_left, crop_h, crop_w)) return 0;
+  const ResizePlan p = make_resize_plan(H, W, resized_h, resized_w, crop_top, crop_left, crop_h, crop_w);
+  return p.ok ? p.table_bytes : 0;
+}
+
+int b200ir_resize_crop(const uint8_t* img, int64_t B, int H, int W, int resized_h, int resized_w, int crop_top,
+                       int crop_left, int crop_h, int crop_w, uint8_t* out, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  if (B < 0 || !resize_args_ok(H, W, resized_h, resized_w, crop_top, crop_left, crop_h, crop_w)) return B200IR_E_ARG;
+  if (B == 0) return 0;
+  if (!img || !out) return B200IR_E_ARG;
+  const ResizePlan p = make_resize_plan(H, W, resized_h, resized_w, crop_top, crop_left, crop_h, crop_w);
+  if (!p.ok) return B200IR_E_SHAPE;                 // down-scale factor too large for the shared-memory tile
+  if (!workspace || workspace_bytes < p.table_bytes) return B200IR_E_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return B200IR_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope ps(PT_RESIZE, st);
+  return int(run_resize_crop(p, img, B, H, W, crop_h, crop_w, out, static_cast<unsigned char*>(workspace), st));
 }
 
 int b200ir_counts_to_embedding(const uint32_t* counts, int64_t B, int nb, float* raw_out, float* unit_out,

@@ -6,7 +6,7 @@
 namespace b200ir {
 
 enum ProfileTag { PT_PREP = 0, PT_SCAN = 1, PT_GEMM = 2, PT_FINALIZE = 3, PT_RERANK = 4, PT_MERGE = 5, PT_HIST = 6,
-                  PT_MISC = 7, PT_COUNT = 8 };
+                  PT_MISC = 7, PT_RESIZE = 8, PT_COUNT = 9 };
 
 void profile_begin(int tag, cudaStream_t st);   // counts the launch; records an event when enabled
 void profile_end(int tag, cudaStream_t st);

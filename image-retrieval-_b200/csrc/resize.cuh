@@ -1,0 +1,326 @@
+// Image front-end of the embedding producer: bicubic resize + centre crop of uint8 RGB images, bit-exact with the
+// PIL path the reference's CLIPProcessor takes (ImageEmbeddingSystem.py:82-83; Pillow libImaging/Resample.c:
+// separable, horizontal pass first into uint8, 22-bit fixed-point coefficients, clip8((2^21 + sum) >> 22)).
+//
+// One fused kernel: a CTA owns `rows_per_block` output rows of one image.  It streams the input rows its vertical
+// windows touch through a small row buffer (16-byte loads, kRowBatch rows per barrier pair), resamples each row
+// horizontally for the cropped columns only into a shared uint8 tile, then runs the vertical pass out of that tile.
+// The intermediate image never reaches HBM; source bytes are read once per CTA (neighbouring CTAs re-read the
+// ~2*support overlap rows, normally out of L2).  Coefficient tables are built on the host in double, exactly as
+// Pillow does, and live in the caller's workspace.
+#pragma once
+#include "common.cuh"
+
+#include <math.h>
+#include <vector>
+
+namespace b200ir {
+
+constexpr int kResizePrecisionBits = 32 - 8 - 2;
+constexpr int kResizeThreads = 256;
+constexpr int kRowBatch = 8;
+constexpr int kResizeSmemBudget = 160 * 1024;
+
+struct ResampleTable {
+  int ksize = 0;
+  std::vector<int32_t> bounds;   // [count][2]: first input coordinate, tap count
+  std::vector<int32_t> kk;       // [count][ksize]
+  int in_lo = 0, in_hi = 0;      // input span [in_lo, in_hi) touched by the table
+};
+
+inline double bicubic_weight(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+// Coefficients of output coordinates [first, first + count) when `in_size` samples are resampled to `out_size`.
+inline ResampleTable make_resample_table(int in_size, int out_size, int first, int count) {
+  ResampleTable t;
+  t.bounds.resize(size_t(count) * 2);
+  if (in_size == out_size) {                      // Pillow skips the pass: identity taps
+    t.ksize = 1;
+    t.kk.assign(size_t(count), 1 << kResizePrecisionBits);
+    for (int i = 0; i < count; ++i) { t.bounds[2 * i] = first + i; t.bounds[2 * i + 1] = 1; }
+    t.in_lo = first; t.in_hi = first + count;
+    return t;
+  }
+  const double scale = double(in_size) / double(out_size);
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * filterscale;
+  t.ksize = int(ceil(support)) * 2 + 1;
+  t.kk.assign(size_t(count) * t.ksize, 0);
+  const double ss = 1.0 / filterscale;
+  std::vector<double> w(size_t(t.ksize));
+  t.in_lo = in_size; t.in_hi = 0;
+  for (int i = 0; i < count; ++i) {
+    const int xx = first + i;
+    const double center = (xx + 0.5) * scale;
+    int xmin = int(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = int(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      w[x] = bicubic_weight((x + xmin - center + 0.5) * ss);
+      ww += w[x];
+    }
+    for (int x = 0; x < xmax; ++x) {
+      const double v = ww != 0.0 ? w[x] / ww : w[x];
+      t.kk[size_t(i) * t.ksize + x] = v < 0 ? int(-0.5 + v * (1 << kResizePrecisionBits)) : int(0.5 + v * (1 << kResizePrecisionBits));
+    }
+    t.bounds[2 * i] = xmin;
+    t.bounds[2 * i + 1] = xmax;
+    if (xmin < t.in_lo) t.in_lo = xmin;
+    if (xmin + xmax > t.in_hi) t.in_hi = xmin + xmax;
+  }
+  return t;
+}
+
+struct ResizePlan {
+  ResampleTable tx, ty;
+  int rows_per_block = 0, max_rows = 0, row_buf_bytes = 0;
+  size_t smem_bytes = 0, table_bytes = 0;
+  size_t off_xb = 0, off_xk = 0, off_yb = 0, off_yk = 0;
+  bool ok = false;
+};
+
+inline ResizePlan make_resize_plan(int H, int W, int rh, int rw, int top, int left, int ch, int cw) {
+  ResizePlan p;
+  p.tx = make_resample_table(W, rw, left, cw);
+  p.ty = make_resample_table(H, rh, top, ch);
+  p.row_buf_bytes = int(round_up64(int64_t(p.tx.in_hi - p.tx.in_lo) * 3 + 16 + 48, 16));   // +48: fixed-trip tap loops read past the span
+  const int64_t out_row = int64_t(cw) * 3;
+  // the largest group of output rows whose input-row window (tile) + row buffers fit the shared-memory budget
+  for (int rpb = 16; rpb >= 1; rpb >>= 1) {
+    int max_rows = 0;
+    for (int y0 = 0; y0 < ch; y0 += rpb) {
+      const int y1 = (y0 + rpb < ch ? y0 + rpb : ch) - 1;
+      const int rows = p.ty.bounds[2 * y1] + p.ty.bounds[2 * y1 + 1] - p.ty.bounds[2 * y0];
+      if (rows > max_rows) max_rows = rows;
+    }
+    const size_t smem = size_t(kRowBatch) * p.row_buf_bytes + size_t(max_rows) * size_t(round_up64(out_row, 4)) +
+                        size_t(rpb) * (2 + p.ty.ksize) * 4;
+    if (smem <= size_t(kResizeSmemBudget)) {
+      p.rows_per_block = rpb; p.max_rows = max_rows; p.smem_bytes = smem; p.ok = true;
+      break;
+    }
+  }
+  size_t off = 0;
+  auto take = [&off](size_t n) { size_t o = off; off += size_t(round_up64(int64_t(n), 256)); return o; };
+  p.off_xb = take(p.tx.bounds.size() * 4);
+  p.off_xk = take(p.tx.kk.size() * 4);
+  p.off_yb = take(p.ty.bounds.size() * 4);
+  p.off_yk = take(p.ty.kk.size() * 4);
+  p.table_bytes = off;
+  return p;
+}
+
+struct ResizeArgs {
+  const uint8_t* img; uint8_t* out;
+  int64_t img_stride;              // bytes per input image
+  int H, W, cw, ch, kx, ky, rows_per_block, row_buf_bytes, x_lo, x_hi, tile_pitch, max_rows, word_out;
+  const int32_t *xb, *xk, *yb, *yk;
+};
+
+__device__ __forceinline__ uint8_t clip8(int v) {
+  v >>= kResizePrecisionBits;
+  return uint8_t(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// KREG > 0: horizontal taps of "this thread's" output column live in KREG registers (kx <= KREG, cw <= kResizeThreads;
+// table entries past the tap count are zero and the row buffers are padded, so the tap loop has a fixed trip count).
+// KREG == 0: any geometry, taps read through the read-only cache.
+template <int KREG>
+__global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs a) {
+  extern __shared__ __align__(16) uint8_t rs_smem[];
+  uint8_t* rowbuf = rs_smem;                                     // kRowBatch x row_buf_bytes
+  uint8_t* tile = rs_smem + kRowBatch * a.row_buf_bytes;         // max_rows x tile_pitch (horizontally resampled rows)
+  int32_t* ksm = reinterpret_cast<int32_t*>(tile + a.max_rows * a.tile_pitch);   // rows_per_block x (2 + ky): vertical taps
+  const int tid = threadIdx.x;
+  const int y0 = blockIdx.x * a.rows_per_block;
+  const int y1 = min(a.ch, y0 + a.rows_per_block);
+  const int r0 = a.yb[2 * y0];
+  const int r1 = a.yb[2 * (y1 - 1)] + a.yb[2 * (y1 - 1) + 1];
+  const uint8_t* img = a.img + int64_t(blockIdx.y) * a.img_stride;
+  const int out_row = a.cw * 3;
+  const int64_t seg_off = int64_t(a.x_lo) * 3;
+  const int seg_bytes = (a.x_hi - a.x_lo) * 3;
+
+  for (int i = tid; i < (y1 - y0) * (2 + a.ky); i += kResizeThreads) {
+    const int yy = i / (2 + a.ky), j = i - yy * (2 + a.ky);
+    ksm[i] = j < 2 ? a.yb[2 * (y0 + yy) + j] : a.yk[(y0 + yy) * a.ky + j - 2];
+  }
+  int kreg[KREG > 0 ? KREG : 1];
+  int my_off = 0;
+  if (KREG > 0 && tid < a.cw) {
+#pragma unroll
+    for (int j = 0; j < KREG; ++j) kreg[j] = j < a.kx ? a.xk[tid * a.kx + j] : 0;
+    my_off = (a.xb[2 * tid] - a.x_lo) * 3;
+  }
+
+  for (int rb = r0; rb < r1; rb += kRowBatch) {
+    const int nrows = min(kRowBatch, r1 - rb);
+    // stage the needed byte span of up to kRowBatch input rows, one warp per row; 16-byte loads from the aligned
+    // address below the span
+    for (int r = tid >> 5; r < nrows; r += kResizeThreads / 32) {
+      const uint8_t* src = img + (int64_t(rb + r) * a.W) * 3 + seg_off;
+      const int mis = int(reinterpret_cast<uintptr_t>(src) & 15);
+      const uint4* src16 = reinterpret_cast<const uint4*>(src - mis);
+      uint4* dst16 = reinterpret_cast<uint4*>(rowbuf + r * a.row_buf_bytes);
+      const int n16 = (mis + seg_bytes + 15) >> 4;
+      // the last 16-byte load may run past the image; it stays inside the allocation except for the final row of the
+      // final image, which is read bytewise
+      const bool tail_safe = rb + r + 1 < a.H || blockIdx.y + 1 < gridDim.y;
+      const int n_fast = tail_safe ? n16 : n16 - 1;
+      for (int i = tid & 31; i < n_fast; i += 32) dst16[i] = __ldg(src16 + i);
+      if (!tail_safe && (tid & 31) == 0) {
+        uint8_t* d = reinterpret_cast<uint8_t*>(dst16 + n_fast);
+        const uint8_t* s = reinterpret_cast<const uint8_t*>(src16 + n_fast);
+        const int valid = mis + seg_bytes - n_fast * 16;
+        for (int b = 0; b < 16; ++b) d[b] = b < valid ? s[b] : 0;
+      }
+    }
+    __syncthreads();
+    if (KREG > 0) {
+      if (tid < a.cw) {
+        for (int r = 0; r < nrows; ++r) {
+          const uint8_t* src = img + (int64_t(rb + r) * a.W) * 3 + seg_off;
+          // the 3*KREG bytes of this pixel's window: aligned 32-bit shared loads, re-aligned with one PRMT per word
+          // (byte loads would make the kernel LSU-bound: 3 shared loads per tap)
+          const int off = int(reinterpret_cast<uintptr_t>(src) & 15) + my_off;
+          const uint32_t* pw = reinterpret_cast<const uint32_t*>(rowbuf + r * a.row_buf_bytes + (off & ~3));
+          const uint32_t sel = 0x3210u + 0x1111u * uint32_t(off & 3);
+          constexpr int NW = (3 * KREG + 3) / 4;
+          uint32_t w[NW + 1];
+#pragma unroll
+          for (int i = 0; i <= NW; ++i) w[i] = pw[i];
+#pragma unroll
+          for (int i = 0; i < NW; ++i) w[i] = __byte_perm(w[i], w[i + 1], sel);
+          int acc0 = 1 << (kResizePrecisionBits - 1), acc1 = acc0, acc2 = acc0;
+#pragma unroll
+          for (int j = 0; j < KREG; ++j) {
+            acc0 += int(__byte_perm(w[(3 * j) >> 2], 0, 0x4440u + ((3 * j) & 3))) * kreg[j];
+            acc1 += int(__byte_perm(w[(3 * j + 1) >> 2], 0, 0x4440u + ((3 * j + 1) & 3))) * kreg[j];
+            acc2 += int(__byte_perm(w[(3 * j + 2) >> 2], 0, 0x4440u + ((3 * j + 2) & 3))) * kreg[j];
+          }
+          uint8_t* t = tile + (rb - r0 + r) * a.tile_pitch + tid * 3;
+          t[0] = clip8(acc0); t[1] = clip8(acc1); t[2] = clip8(acc2);
+        }
+      }
+    } else {
+      for (int o = tid; o < nrows * a.cw; o += kResizeThreads) {      // one thread = one pixel (3 channels share the taps)
+        const int r = o / a.cw, xx = o - r * a.cw;
+        const uint8_t* src = img + (int64_t(rb + r) * a.W) * 3 + seg_off;
+        const int mis = int(reinterpret_cast<uintptr_t>(src) & 15);
+        const int xmin = a.xb[2 * xx], n = a.xb[2 * xx + 1];
+        const uint8_t* px = rowbuf + r * a.row_buf_bytes + mis + (xmin - a.x_lo) * 3;
+        const int32_t* k = a.xk + xx * a.kx;
+        int acc0 = 1 << (kResizePrecisionBits - 1), acc1 = acc0, acc2 = acc0;
+        for (int j = 0; j < n; ++j) {
+          const int w = __ldg(k + j);
+          acc0 += int(px[j * 3]) * w;
+          acc1 += int(px[j * 3 + 1]) * w;
+          acc2 += int(px[j * 3 + 2]) * w;
+        }
+        uint8_t* t = tile + (rb - r0 + r) * a.tile_pitch + xx * 3;
+        t[0] = clip8(acc0); t[1] = clip8(acc1); t[2] = clip8(acc2);
+      }
+    }
+    __syncthreads();
+  }
+  // vertical pass out of the tile: one thread = 4 consecutive bytes of an output row, taps broadcast from shared memory
+  uint8_t* out = a.out + (int64_t(blockIdx.y) * a.ch + y0) * out_row;
+  if (a.word_out) {
+    const int words = out_row >> 2, pitch4 = a.tile_pitch >> 2;
+    const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
+    for (int wd = tid; wd < words; wd += kResizeThreads) {
+      for (int yy = 0; yy < y1 - y0; ++yy) {
+        const int32_t* k = ksm + yy * (2 + a.ky);
+        const int n = k[1];
+        const uint32_t* px = tile32 + (k[0] - r0) * pitch4 + wd;
+        int acc0 = 1 << (kResizePrecisionBits - 1), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+          const uint32_t w = px[j * pitch4];
+          const int kj = k[2 + j];
+          acc0 += int(__byte_perm(w, 0, 0x4440u)) * kj;
+          acc1 += int(__byte_perm(w, 0, 0x4441u)) * kj;
+          acc2 += int(__byte_perm(w, 0, 0x4442u)) * kj;
+          acc3 += int(w >> 24) * kj;
+        }
+        reinterpret_cast<uint32_t*>(out)[yy * words + wd] = uint32_t(clip8(acc0)) | (uint32_t(clip8(acc1)) << 8) |
+                                                             (uint32_t(clip8(acc2)) << 16) | (uint32_t(clip8(acc3)) << 24);
+      }
+    }
+  } else {
+    for (int o = tid; o < (y1 - y0) * out_row; o += kResizeThreads) {
+      const int yy = o / out_row, e = o - yy * out_row;
+      const int32_t* k = ksm + yy * (2 + a.ky);
+      const int n = k[1];
+      const uint8_t* px = tile + (k[0] - r0) * a.tile_pitch + e;
+      int acc = 1 << (kResizePrecisionBits - 1);
+      for (int j = 0; j < n; ++j) acc += int(px[j * a.tile_pitch]) * k[2 + j];
+      out[o] = clip8(acc);
+    }
+  }
+}
+
+template <int KREG>
+inline cudaError_t launch_resize_crop(const ResizeArgs& a, int groups, int nb, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(resize_crop_kernel<KREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kResizeSmemBudget);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  resize_crop_kernel<KREG><<<dim3(groups, nb), kResizeThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+inline cudaError_t run_resize_crop(const ResizePlan& p, const uint8_t* img, int64_t B, int H, int W, int ch, int cw,
+                                   uint8_t* out, unsigned char* ws, cudaStream_t st) {
+  cudaError_t e;
+  // pageable -> device async copies are staged before the call returns, so the host vectors may die with the plan
+  if ((e = cudaMemcpyAsync(ws + p.off_xb, p.tx.bounds.data(), p.tx.bounds.size() * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(ws + p.off_xk, p.tx.kk.data(), p.tx.kk.size() * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(ws + p.off_yb, p.ty.bounds.data(), p.ty.bounds.size() * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(ws + p.off_yk, p.ty.kk.data(), p.ty.kk.size() * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+  ResizeArgs a;
+  a.img = img; a.out = out;
+  a.img_stride = int64_t(H) * W * 3;
+  a.H = H; a.W = W; a.cw = cw; a.ch = ch; a.kx = p.tx.ksize; a.ky = p.ty.ksize;
+  a.rows_per_block = p.rows_per_block; a.row_buf_bytes = p.row_buf_bytes;
+  a.x_lo = p.tx.in_lo; a.x_hi = p.tx.in_hi;
+  a.tile_pitch = int(round_up64(int64_t(cw) * 3, 4));
+  a.xb = reinterpret_cast<const int32_t*>(ws + p.off_xb);
+  a.xk = reinterpret_cast<const int32_t*>(ws + p.off_xk);
+  a.yb = reinterpret_cast<const int32_t*>(ws + p.off_yb);
+  a.yk = reinterpret_cast<const int32_t*>(ws + p.off_yk);
+  a.max_rows = p.max_rows;
+  a.word_out = (cw * 3) % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 4 == 0 ? 1 : 0;
+  const int kreg = cw <= kResizeThreads ? (a.kx <= 5 ? 5 : a.kx <= 7 ? 7 : a.kx <= 9 ? 9 : a.kx <= 11 ? 11 : a.kx <= 13 ? 13 : a.kx <= 15 ? 15 : 0) : 0;
+  const int groups = int(ceil_div64(ch, p.rows_per_block));
+  for (int64_t b0 = 0; b0 < B; b0 += 65535) {          // gridDim.y limit
+    const int nb = int(B - b0 < 65535 ? B - b0 : 65535);
+    ResizeArgs ab = a;
+    ab.img = img + b0 * a.img_stride;
+    ab.out = out + b0 * int64_t(ch) * cw * 3;
+    switch (kreg) {
+      case 5: e = launch_resize_crop<5>(ab, groups, nb, p.smem_bytes, st); break;
+      case 7: e = launch_resize_crop<7>(ab, groups, nb, p.smem_bytes, st); break;
+      case 9: e = launch_resize_crop<9>(ab, groups, nb, p.smem_bytes, st); break;
+      case 11: e = launch_resize_crop<11>(ab, groups, nb, p.smem_bytes, st); break;
+      case 13: e = launch_resize_crop<13>(ab, groups, nb, p.smem_bytes, st); break;
+      case 15: e = launch_resize_crop<15>(ab, groups, nb, p.smem_bytes, st); break;
+      default: e = launch_resize_crop<0>(ab, groups, nb, p.smem_bytes, st); break;
+    }
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace b200ir

@@ -255,6 +255,43 @@ def pair_metrics(A, B, ia, ib):
     return out
 
 
+def shortest_edge_size(H, W, size=224):
+    """(new_h, new_w) when the shorter edge goes to `size` (CLIPProcessor's resize rule: new_long = int(size * long / short))."""
+    short, long = (W, H) if W <= H else (H, W)
+    new_long = int(size * long / short)
+    return (new_long, size) if W <= H else (size, new_long)
+
+
+def resize_crop(images, size=224, resized=None, crop=None):
+    """(B,H,W,3) uint8 -> (B,size,size,3) uint8 on the device: PIL-exact bicubic resize of the shorter edge to `size`,
+    then centre crop (the reference's CLIPProcessor front-end, ImageEmbeddingSystem.py:82-83).  `resized=(h, w)` and
+    `crop=(top, left, h, w)` override the rule."""
+    dev = device()
+    if isinstance(images, np.ndarray):
+        images = torch.from_numpy(np.ascontiguousarray(images))
+    if images.dtype != torch.uint8:
+        raise ValueError("images must be uint8")
+    if images.dim() == 3:
+        images = images.unsqueeze(0)
+    if images.dim() != 4 or images.shape[-1] != 3:
+        raise ValueError(f"expected (B,H,W,3) uint8, got {tuple(images.shape)}")
+    if images.device != dev:
+        images = images.to(dev, non_blocking=True)
+    images = images.contiguous()
+    B, H, W, _ = images.shape
+    rh, rw = shortest_edge_size(H, W, size) if resized is None else resized
+    top, left, ch, cw = ((rh - size) // 2, (rw - size) // 2, size, size) if crop is None else crop
+    lib = _lib.load()
+    need = lib.b200ir_resize_crop_workspace_bytes(H, W, rh, rw, top, left, ch, cw)
+    if need == 0:
+        raise ValueError(f"resize_crop: unsupported geometry {(H, W)} -> {(rh, rw)} crop {(top, left, ch, cw)}")
+    ws = _workspace(need, dev)
+    out = torch.empty((B, ch, cw, 3), dtype=torch.uint8, device=dev)
+    _lib.check(lib.b200ir_resize_crop(_ptr(images), B, H, W, rh, rw, top, left, ch, cw, _ptr(out), _ptr(ws), ws.numel(), _stream()),
+               "resize_crop")
+    return out
+
+
 def histogram(images, colorspace="rgb"):
     """(B,H,W,3) uint8 RGB -> (B,512) int32 counts on the device (8x8x8 joint bins)."""
     dev = device()

@@ -156,6 +156,20 @@ int b200ir_pair_metrics(int dtype, const void* A, int64_t NA, const void* B, int
                         const int64_t* ia, const int64_t* ib, int64_t P, float* out, void* stream);
 
 /*
+ * Image front-end of the embedding producer (ImageEmbeddingSystem.py:82-83, app_pipeline.py:127-131: PIL image ->
+ * CLIPProcessor = resize shorter edge to 224 with PIL BICUBIC, centre crop 224 x 224).  img [B, H, W, 3] uint8 is
+ * resized to resized_h x resized_w with Pillow's 8-bit bicubic arithmetic (bit-exact: horizontal pass first, 22-bit
+ * fixed-point taps) and the window [crop_top, crop_top + crop_h) x [crop_left, crop_left + crop_w) of the result is
+ * written to out [B, crop_h, crop_w, 3]; only that window is computed.  The workspace holds the tap tables.
+ * B200IR_E_SHAPE when the vertical down-scale factor is too large for the on-chip tile (> ~80x).
+ */
+size_t b200ir_resize_crop_workspace_bytes(int H, int W, int resized_h, int resized_w, int crop_top, int crop_left,
+                                          int crop_h, int crop_w);
+int b200ir_resize_crop(const uint8_t* img, int64_t B, int H, int W, int resized_h, int resized_w, int crop_top,
+                       int crop_left, int crop_h, int crop_w, uint8_t* out, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/*
  * 512-bin joint colour histogram of uint8 images, img [B, H, W, 3] interleaved RGB,
  * out_counts [B, bins^3] uint32, bin = (c0bin*bins + c1bin)*bins + c2bin with
  * c*bin = c>>5 (H: h*8/180).  bins_per_channel must be 8.  The embedding producer
@@ -176,7 +190,7 @@ int b200ir_counts_to_embedding(const uint32_t* counts, int64_t B, int nb,
  * Measurement hooks (bench.py).  b200ir_launch_count: kernels launched by this library since load.
  * b200ir_profile_enable(1) brackets every kernel launch with CUDA events on the launching stream;
  * b200ir_profile_read(tag, &ms, &n) synchronises on and drains the events of one kernel class
- * (0 prep, 1 scan, 2 tcgen05 gemm+topk, 3 finalize, 4 rerank, 5 merge, 6 histogram, 7 misc).
+ * (0 prep, 1 scan, 2 tcgen05 gemm+topk, 3 finalize, 4 rerank, 5 merge, 6 histogram, 7 misc, 8 resize).
  */
 long long b200ir_launch_count(void);
 void b200ir_profile_enable(int on);

@@ -10,6 +10,7 @@ Outputs (committed, small):
   metrics_golden.npz  - vectors + every reference metric, pair by pair
   search_golden.npz   - DB/query vectors + reference top-k paths/scores
   hist_golden.npz     - images + cv2.calcHist counts (RGB, HSV)  [OpenCV, not the reference]
+  resize_golden.npz   - PIL Image.resize(BICUBIC) + centre crop of seeded images (the CLIPProcessor front-end)  [Pillow]
   pairs_golden.json   - metadata rows -> the reference's generate_relationship_pairs output, and the per-pair
                         get_all_metrics values of mi_analysis.py:277-291 for seeded embeddings of those paths
 """
@@ -115,6 +116,39 @@ def hist_golden():
                         rgb=np.array(rgb).astype(np.uint32), hsv=np.array(hsv).astype(np.uint32))
 
 
+RESIZE_CASES = [  # (H, W, size, seed, generator)
+    (60, 80, 32, 21, "uniform"), (80, 60, 32, 22, "palette"), (33, 47, 32, 23, "uniform"), (32, 32, 32, 24, "uniform"),
+    (20, 31, 32, 25, "palette"), (300, 32, 32, 26, "uniform"), (32, 301, 32, 27, "uniform"), (1000, 1300, 32, 28, "palette"),
+    (480, 640, 224, 29, "palette")]
+
+
+def resize_golden():
+    """PIL itself: Image.fromarray(img).resize((new_w, new_h), BICUBIC), then the processor's centre crop.  The result
+    equals transformers' CLIPImageProcessorPil(do_rescale=False, do_normalize=False) (checked when available)."""
+    from PIL import Image
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle import synth
+    out = {"cases": np.array([c[:4] for c in RESIZE_CASES], dtype=np.int64), "generators": np.array([c[4] for c in RESIZE_CASES])}
+    for n, (H, W, size, seed, gen) in enumerate(RESIZE_CASES):
+        img = getattr(synth, f"images_{gen}")(1, H, W, seed)[0]
+        short, long = (W, H) if W <= H else (H, W)
+        new_long = int(size * long / short)
+        nh, nw = (new_long, size) if W <= H else (size, new_long)
+        r = np.asarray(Image.fromarray(img).resize((nw, nh), resample=Image.BICUBIC))
+        top, left = (nh - size) // 2, (nw - size) // 2
+        crop = r[top:top + size, left:left + size]
+        try:
+            from transformers import CLIPImageProcessorPil
+            p = CLIPImageProcessorPil(do_rescale=False, do_normalize=False, do_convert_rgb=False, size={"shortest_edge": size},
+                                      crop_size={"height": size, "width": size})
+            t = np.moveaxis(np.asarray(p(images=Image.fromarray(img), return_tensors="np")["pixel_values"][0]), 0, -1)
+            assert np.array_equal(t, crop), (H, W, size)
+        except ImportError:
+            pass
+        out[f"out_{n}"] = crop
+    np.savez_compressed(os.path.join(HERE, "resize_golden.npz"), **out)
+
+
 def pairs_golden():
     """ColorDatasetManager.generate_relationship_pairs (imageProcessing.py:296-387) run on hand-made metadata, then the
     calculate_distances loop body (mi_analysis.py:277-291; mi_analysis itself needs matplotlib and cannot be imported)."""
@@ -153,7 +187,8 @@ def pairs_golden():
 
 if __name__ == "__main__":
     pairs_golden()
-    if "--pairs-only" in sys.argv:
+    resize_golden()
+    if "--new-only" in sys.argv:
         sys.exit(0)
     metrics_golden()
     search_golden()

@@ -514,3 +514,43 @@ def test_pair_metrics_match_oracle(ops, D, dtype):
     same = ops.pair_metrics(tA, None, [1, 2], [2, 1]).cpu().numpy()                          # symmetric within one store
     assert np.array_equal(same[:, 0], same[:, 1])
     assert ops.pair_metrics(tA, None, [], []).shape == (7, 0)
+
+
+# ------------------------------------------------------------------------------- image front-end
+def test_resize_crop_bit_exact_pil_golden(ops, golden_dir):
+    """b200ir_resize_crop == PIL BICUBIC resize + centre crop (fixtures written by PIL, tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "resize_golden.npz"))
+    for n, ((H, W, size, seed), gen) in enumerate(zip(g["cases"], g["generators"])):
+        img = getattr(synth, f"images_{gen}")(1, int(H), int(W), int(seed))[0]
+        got = ops.resize_crop(img, int(size)).cpu().numpy()
+        assert got.shape == (1, size, size, 3)
+        assert np.array_equal(got[0], g[f"out_{n}"]), (H, W, size)
+
+
+@pytest.mark.parametrize("H,W,size", [(480, 640, 224), (640, 480, 224), (224, 224, 224), (100, 150, 224), (333, 517, 224),
+                                      (225, 300, 224), (50, 37, 64), (1200, 900, 224), (224, 500, 224), (3000, 2000, 224)])
+def test_resize_crop_bit_exact_oracle(ops, H, W, size):
+    from oracle import resize as R
+    imgs = np.concatenate([synth.images_uniform(2, H, W, H + W), synth.images_palette(1, H, W, H * W)])
+    got = ops.resize_crop(imgs, size).cpu().numpy()
+    for b in range(3):
+        assert np.array_equal(got[b], R.clip_preprocess_u8(imgs[b], size)), b
+    # unaligned device view (odd byte offset) and an explicit window of the resized image
+    import torch
+    flat = torch.zeros(imgs[0].size + 5, dtype=torch.uint8, device="cuda")
+    flat[5:] = torch.from_numpy(imgs[0]).cuda().view(-1)
+    view = flat[5:].view(1, H, W, 3)
+    nh, nw = R.shortest_edge_size(H, W, size)
+    win = (nh // 3, nw // 4, min(17, nh - nh // 3), min(29, nw - nw // 4))
+    got = ops.resize_crop(view, size, crop=win).cpu().numpy()[0]
+    want = R.resize_bicubic(imgs[0], nh, nw)[win[0]:win[0] + win[2], win[1]:win[1] + win[3]]
+    assert np.array_equal(got, want)
+
+
+def test_resize_then_histogram_pipeline(ops):
+    """front-end + embedding producer: histogram(resize_crop(img)) == oracle histogram of the oracle-resized image."""
+    from oracle import resize as R
+    imgs = synth.images_palette(4, 300, 400, 77)
+    counts = ops.histogram(ops.resize_crop(imgs, 224), "rgb").cpu().numpy()
+    for b in range(4):
+        assert np.array_equal(counts[b], OH.histogram(R.clip_preprocess_u8(imgs[b], 224)[None], "rgb")[0])

@@ -8,6 +8,7 @@ import pytest
 from oracle import histogram as H
 from oracle import metrics as M
 from oracle import search as S
+from oracle import synth
 
 DIMS = (1, 3, 7, 64, 512, 2048)
 PARAMS = {"w_angle": 1.0, "w_l1": 1.0, "w_l2": 1.0, "w_inf": 0.0, "w_mag": 0.5}
@@ -186,3 +187,27 @@ def test_pair_list_distances_match_reference_run(golden_dir):
     for m in E.METRICS:
         for r in E.RELATIONSHIP_TYPES:
             assert [float(x) for x in d[m][r]] == g["distances"][m][r], (m, r)
+
+
+def _resize_cases(golden_dir):
+    g = np.load(os.path.join(golden_dir, "resize_golden.npz"))
+    for n, ((H, W, size, seed), gen) in enumerate(zip(g["cases"], g["generators"])):
+        img = getattr(synth, f"images_{gen}")(1, int(H), int(W), int(seed))[0]
+        yield img, int(size), g[f"out_{n}"]
+
+
+def test_resize_oracle_matches_pil_golden(golden_dir):
+    """Pillow's 8-bit bicubic resample restated in oracle/resize.py == PIL's own output (make_golden.resize_golden)."""
+    from oracle import resize as R
+    for img, size, want in _resize_cases(golden_dir):
+        assert np.array_equal(R.clip_preprocess_u8(img, size), want), img.shape
+
+
+def test_resize_oracle_matches_pil_live():
+    Image = pytest.importorskip("PIL.Image")
+    from oracle import resize as R
+    for H, W, size, seed in [(97, 131, 48, 1), (131, 97, 48, 2), (500, 375, 224, 3), (40, 40, 64, 4)]:
+        img = synth.images_palette(1, H, W, seed)[0]
+        nh, nw = R.shortest_edge_size(H, W, size)
+        pil = np.asarray(Image.fromarray(img).resize((nw, nh), resample=Image.BICUBIC))
+        assert np.array_equal(R.resize_bicubic(img, nh, nw), pil)
