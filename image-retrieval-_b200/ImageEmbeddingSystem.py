@@ -6,7 +6,9 @@ get_embeddings, get_embeddings_with_magnitude, reconstruct_original_embeddings, 
 skip-and-count error behaviour.  Replaced: the CLIP image tower by the 512-bin colour-histogram
 kernel north_star names (EMBEDDING_DIM = 8*8*8), and the Milvus collection by an HBM-resident
 matrix (store.EmbeddingStore).  `model` / `processor` are accepted for signature compatibility
-and ignored.
+and ignored.  `image_size=224` turns on the processor's image front-end (:82-83: shorter edge -> 224
+with PIL BICUBIC, centre crop 224 x 224) on the device, bit-exact with PIL (ops.resize_crop); the
+default None embeds the image at its own size.
 """
 import logging
 from pathlib import Path
@@ -24,11 +26,12 @@ logger = logging.getLogger(__name__)
 class ImageEmbeddingSystem:
     """Handles image embedding generation and storage (device-resident)."""
 
-    def __init__(self, model=None, processor=None, device: str = "cuda", colorspace: str = "rgb"):
+    def __init__(self, model=None, processor=None, device: str = "cuda", colorspace: str = "rgb", image_size=None):
         self.model = model
         self.processor = processor
         self.device = device
         self.colorspace = colorspace
+        self.image_size = image_size
         self.setup_milvus()
 
     def setup_milvus(self):
@@ -50,6 +53,8 @@ class ImageEmbeddingSystem:
 
     def embed_batch(self, images):
         """(B,H,W,3) uint8 -> (unit (B,512) fp32, magnitude (B,) fp32) device tensors."""
+        if self.image_size is not None and tuple(images.shape[-3:-1]) != (self.image_size, self.image_size):
+            images = ops.resize_crop(images, self.image_size)
         counts = ops.histogram(images, self.colorspace)
         _raw, unit, mag = ops.counts_to_embedding(counts)
         return unit, mag

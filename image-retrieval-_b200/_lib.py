@@ -36,6 +36,8 @@ _SIGNATURES = {
                                               ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double), ctypes.c_int,
                                               c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "b200ir_pair_metrics": (ctypes.c_int, [ctypes.c_int, c_vp, c_i64, c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "b200ir_threshold_dedupe": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_i64, ctypes.c_double, ctypes.c_int,
+                                               ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "b200ir_resize_crop_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 8),
     "b200ir_resize_crop": (ctypes.c_int, [c_vp, c_i64] + [ctypes.c_int] * 8 + [c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "b200ir_histogram": (ctypes.c_int, [ctypes.c_int, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),

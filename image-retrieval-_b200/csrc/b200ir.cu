@@ -6,6 +6,7 @@
 #include "histogram.cuh"
 #include "pairs.cuh"
 #include "resize.cuh"
+#include "postfilter.cuh"
 #include "gemm_topk.h"
 #include "profile.h"
 
@@ -302,6 +303,19 @@ int b200ir_histogram(int colorspace, const uint8_t* img, int64_t B, int H, int W
   } else {
     histogram_kernel<false><<<unsigned(B * slices), kHistThreads, 0, st>>>(img, pixels, slices, vector_ok, out_counts);
   }
+  return int(cudaGetLastError());
+}
+
+int b200ir_threshold_dedupe(const float* score, const int64_t* idx, int64_t nq, int kc, const int64_t* group, int64_t N,
+                            double threshold, int relative, int top_k, float* out_score, int64_t* out_idx,
+                            int32_t* out_count, void* stream) {
+  if (nq < 0 || kc < 1 || kc > kPostMaxCand || top_k < 1 || N < 0 || nq > 0x7fffffff / 32) return B200IR_E_ARG;
+  if (nq == 0) return 0;
+  if (!score || !idx || !out_score || !out_idx) return B200IR_E_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope ps(PT_MISC, st);
+  threshold_dedupe_kernel<<<int(ceil_div64(nq, 4)), 128, 0, st>>>(score, idx, int(nq), kc, group, N, threshold, relative ? 1 : 0,
+                                                                 top_k, out_score, out_idx, out_count);
   return int(cudaGetLastError());
 }
 

@@ -115,6 +115,42 @@ class EnhancedTextImageSearcher:
         logger.info(f"Found {len(unique)} matches")
         return unique[:top_k]
 
+    def _path_groups(self, paths):
+        """(N,) int64 device tensor: rows holding the same path share an id (what `seen_paths` compares, :128-137)."""
+        key = (id(paths), len(paths))
+        if getattr(self, "_groups_key", None) != key:
+            first = {}
+            ids = np.fromiter((first.setdefault(p, i) for i, p in enumerate(paths)), dtype=np.int64, count=len(paths))
+            self._groups = None if len(first) == len(paths) else torch.from_numpy(ids).to(ops.device())
+            self._groups_key = key
+        return self._groups
+
+    def search_batch(self, queries, top_k: int = 5, score_threshold: float = SCORE_THRESHOLD,
+                     use_optimized_similarity: bool = False):
+        """search() for a (nq, D) batch of query vectors with every stage on the device: exact top-3k candidates,
+        threshold, de-duplication by path and the cut to top_k (:88-140).  Returns one result list per query."""
+        Q = ops.as_device_matrix(np.asarray(queries, dtype=np.float32) if not torch.is_tensor(queries) else queries)
+        paths, X = self._store()
+        if X is None or len(paths) == 0:
+            return [[] for _ in range(Q.shape[0])]
+        kc = max(1, min(int(top_k) * 3, len(paths), ops.MAX_K))
+        s, i = ops.topk(Q, X, "cosine_similarity", kc)                    # candidate stage (:88-95)
+        if use_optimized_similarity:
+            # re-score the cosine candidates (:103-107) from one get_all_metrics launch, then the stable sort of :116
+            nq = Q.shape[0]
+            qi = torch.arange(nq, device=i.device).repeat_interleave(kc)
+            v = ops.pair_metrics(Q, X, qi, i.reshape(-1))
+            w = dict(w_angle=1.0, w_l1=0.0, w_l2=0.0, w_inf=0.0, w_mag=0.0)
+            w.update(self.similarity_params or {})
+            sim = (w["w_angle"] * v[0] - w["w_l1"] * v[3] - w["w_l2"] * v[4] - w["w_inf"] * v[5] - w["w_mag"] * v[6]).view(nq, kc)
+            sim = torch.where(i >= 0, sim, torch.full_like(sim, float("-inf")))
+            s, order = torch.sort(sim, dim=1, descending=True, stable=True)
+            i = torch.gather(i, 1, order)
+        fs, fi, cnt = ops.threshold_dedupe(s, i, int(top_k), score_threshold, relative=use_optimized_similarity,
+                                           group=self._path_groups(paths))
+        fs, fi, cnt = fs.cpu().numpy(), fi.cpu().numpy(), cnt.cpu().numpy()
+        return [[{"path": paths[fi[q, j]], "score": fs[q, j]} for j in range(cnt[q])] for q in range(Q.shape[0])]
+
     def search_with_multiple_metrics(self, text_query, top_k: int = 5):
         """Six per-metric rankings of the cosine candidates + overlap analysis (:144-228)."""
         q = self.generate_text_embedding(text_query)

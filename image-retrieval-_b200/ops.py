@@ -255,6 +255,28 @@ def pair_metrics(A, B, ia, ib):
     return out
 
 
+def threshold_dedupe(scores, idx, top_k, threshold, relative=False, group=None):
+    """Batched threshold + de-duplicate-by-path + cut of best-first candidate lists (image_search.py:115-140).
+    scores / idx (nq, kc) as returned by topk for a descending metric; group (N,) int64 path ids or None.
+    Returns (scores (nq, top_k), idx (nq, top_k) padded with -inf / -1, count (nq,) int32)."""
+    dev = device()
+    scores = scores.contiguous()
+    idx = idx.contiguous()
+    nq, kc = scores.shape
+    N = 0
+    if group is not None:
+        group = torch.as_tensor(group, dtype=torch.int64).to(dev).contiguous()
+        N = group.numel()
+    out_s = torch.empty((nq, top_k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, top_k), dtype=torch.int64, device=dev)
+    cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.b200ir_threshold_dedupe(_ptr(scores), _ptr(idx), nq, kc, _ptr(group) if group is not None else None, N,
+                                           float(threshold), 1 if relative else 0, int(top_k), _ptr(out_s), _ptr(out_i), _ptr(cnt),
+                                           _stream()), "threshold_dedupe")
+    return out_s, out_i, cnt
+
+
 def shortest_edge_size(H, W, size=224):
     """(new_h, new_w) when the shorter edge goes to `size` (CLIPProcessor's resize rule: new_long = int(size * long / short))."""
     short, long = (W, H) if W <= H else (H, W)

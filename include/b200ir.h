@@ -156,6 +156,18 @@ int b200ir_pair_metrics(int dtype, const void* A, int64_t NA, const void* B, int
                         const int64_t* ia, const int64_t* ib, int64_t P, float* out, void* stream);
 
 /*
+ * Post-filter of best-first candidate lists, image_search.py:115-140: score [nq, kc] descending with idx [nq, kc]
+ * (padding idx -1 at the end, as b200ir_topk writes it).  Keeps score >= threshold (relative != 0: threshold becomes
+ * min + threshold * (max - min) over the query's list, the rule for the optimized score :118-123), drops an entry when
+ * an earlier one has the same path (group[row], one id per distinct path; NULL: every row is its own path, :128-137)
+ * and writes the first top_k survivors to out_score / out_idx [nq, top_k] (padding -inf / -1) and their number to
+ * out_count [nq] (may be NULL).  kc <= 1024.
+ */
+int b200ir_threshold_dedupe(const float* score, const int64_t* idx, int64_t nq, int kc, const int64_t* group, int64_t N,
+                            double threshold, int relative, int top_k, float* out_score, int64_t* out_idx,
+                            int32_t* out_count, void* stream);
+
+/*
  * Image front-end of the embedding producer (ImageEmbeddingSystem.py:82-83, app_pipeline.py:127-131: PIL image ->
  * CLIPProcessor = resize shorter edge to 224 with PIL BICUBIC, centre crop 224 x 224).  img [B, H, W, 3] uint8 is
  * resized to resized_h x resized_w with Pillow's 8-bit bicubic arithmetic (bit-exact: horizontal pass first, 22-bit

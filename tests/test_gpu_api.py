@@ -170,3 +170,39 @@ def test_color_mi_analyzer_distances_match_reference_run(tmp_path, golden_dir):
     tp, fp, fn = ref[:, 0], ref[:, 1], ref[:, 2]
     assert np.allclose(prec, np.where(tp + fp > 0, tp / np.maximum(tp + fp, 1), 0.0), atol=0.05)
     assert np.allclose(rec, np.where(tp + fn > 0, tp / np.maximum(tp + fn, 1), 0.0), atol=0.05)
+
+
+def test_embedding_system_with_processor_front_end():
+    """image_size=224: mixed-size images go through the PIL-exact resize + centre crop before the histogram
+    (the reference's processor step, ImageEmbeddingSystem.py:82-83)."""
+    from image_retrieval_b200.ImageEmbeddingSystem import ImageEmbeddingSystem
+    from oracle import histogram as OH
+    from oracle import resize as R
+    imgs = [synth.images_palette(1, 120, 160, 5)[0], synth.images_palette(1, 300, 200, 6)[0], synth.images_uniform(1, 120, 160, 7)[0],
+            synth.images_palette(1, 224, 224, 8)[0]]
+    sys_ = ImageEmbeddingSystem(image_size=224)
+    assert sys_.process_and_store_images(imgs) == (4, 0)
+    assert len(sys_.get_embeddings_with_magnitude()) == 4
+    for im in imgs:
+        unit, mag = sys_.generate_embedding(im)
+        ou, om = OH.embedding(R.clip_preprocess_u8(im, 224)[None])
+        np.testing.assert_allclose(unit, ou[0], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(mag, om[0], rtol=1e-6)
+
+
+def test_search_batch_equals_search_per_query():
+    """EnhancedTextImageSearcher.search_batch (device threshold + dedupe) == search() query by query, with duplicate paths."""
+    from image_retrieval_b200.image_search import EnhancedTextImageSearcher
+    X = synth.gaussian(400, 64, 9, normalize=True)
+    paths = [f"img{i % 150}.jpg" for i in range(400)]            # every path stored 2-3 times
+    Q = X[:12] + 0.4 * synth.gaussian(12, 64, 10, normalize=True)
+    searcher = EnhancedTextImageSearcher(collection=(paths, X))
+    for opt in (False, True):
+        if opt:
+            searcher.set_similarity_params({"w_angle": 1.0, "w_l1": 0.5, "w_l2": 0.0, "w_inf": 0.0, "w_mag": 0.0})
+        batch = searcher.search_batch(Q, top_k=6, score_threshold=0.3, use_optimized_similarity=opt)
+        for q in range(12):
+            single = searcher.search(Q[q], top_k=6, score_threshold=0.3, use_optimized_similarity=opt)
+            assert [r["path"] for r in batch[q]] == [r["path"] for r in single], (opt, q)
+            np.testing.assert_allclose([r["score"] for r in batch[q]], [r["score"] for r in single], rtol=1e-5, atol=2e-6)
+            assert len({r["path"] for r in batch[q]}) == len(batch[q]) <= 6

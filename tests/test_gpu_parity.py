@@ -554,3 +554,34 @@ def test_resize_then_histogram_pipeline(ops):
     counts = ops.histogram(ops.resize_crop(imgs, 224), "rgb").cpu().numpy()
     for b in range(4):
         assert np.array_equal(counts[b], OH.histogram(R.clip_preprocess_u8(imgs[b], 224)[None], "rgb")[0])
+
+
+# ------------------------------------------------------------------------------- post-filter
+@pytest.mark.parametrize("relative", [False, True])
+@pytest.mark.parametrize("kc,top_k", [(15, 5), (96, 32), (256, 100), (7, 10)])
+def test_threshold_dedupe_matches_oracle(ops, kc, top_k, relative):
+    """b200ir_threshold_dedupe == image_search.py:115-140 (oracle.search.threshold_and_dedupe) per query."""
+    import torch
+    rng = np.random.default_rng(kc * 7 + top_k)
+    nq, N = 41, 500
+    group = rng.integers(0, 120, size=N)                       # ~4 rows per path: many duplicates
+    group = np.array([np.flatnonzero(group == g)[0] for g in group], dtype=np.int64)
+    sc = np.sort(rng.uniform(-0.2, 1.0, size=(nq, kc)).astype(np.float32), axis=1)[:, ::-1].copy()
+    sc[3, 2:6] = sc[3, 2]                                       # ties
+    idx = np.stack([rng.permutation(N)[:kc] for _ in range(nq)]).astype(np.int64)
+    nvalid = rng.integers(0, kc + 1, size=nq); nvalid[0] = 0; nvalid[1] = kc
+    for q in range(nq):
+        idx[q, nvalid[q]:] = -1
+        sc[q, nvalid[q]:] = -np.inf
+    thr = 0.25
+    for grp in (group, None):
+        fs, fi, cnt = ops.threshold_dedupe(torch.from_numpy(sc).cuda(), torch.from_numpy(idx).cuda(), top_k, thr, relative, grp)
+        fs, fi, cnt = fs.cpu().numpy(), fi.cpu().numpy(), cnt.cpu().numpy()
+        for q in range(nq):
+            matches = [{"path": int(group[idx[q, j]]) if grp is not None else int(idx[q, j]), "score": sc[q, j], "row": int(idx[q, j])}
+                       for j in range(nvalid[q])]
+            want = OS.threshold_and_dedupe(matches, top_k, thr, relative)
+            assert cnt[q] == len(want), (q, cnt[q], len(want))
+            assert [int(r) for r in fi[q, :cnt[q]]] == [m["row"] for m in want]
+            assert np.array_equal(fs[q, :cnt[q]], np.array([m["score"] for m in want], np.float32))
+            assert (fi[q, cnt[q]:] == -1).all() and np.isneginf(fs[q, cnt[q]:]).all()
