@@ -57,9 +57,11 @@ constexpr int kEvalTQ = 8;
 inline size_t scan_stage_bytes(int TQ, int DKE) {
   return size_t(kScanThreads) * kRowChunkBytes + size_t(round_up64(size_t(TQ) * DKE * 4, 1024));
 }
+// density bins in shared memory: 16-bit counters, two per 32-bit word
+__host__ __device__ inline int eval_hist_words(int nbins) { return (kEvalMetrics * 4 * nbins + 1) / 2; }
 inline size_t eval_smem_bytes(int nbins, int nthr) {
   return size_t(kScanStages) * scan_stage_bytes(kEvalTQ, 32) +
-         size_t(kEvalMetrics) * 4 * nbins * 4 + size_t(kEvalMetrics) * 2 * (nthr + 1) * 4 + size_t(nthr) * 8 + 16 + 64;
+         size_t(eval_hist_words(nbins)) * 4 + size_t(kEvalMetrics) * 2 * (nthr + 1) * 4 + size_t(nthr) * 8 + 16 + 64;
 }
 cudaError_t launch_scan_eval_f32(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, size_t smem, cudaStream_t st);
 

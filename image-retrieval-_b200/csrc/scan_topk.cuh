@@ -116,14 +116,32 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
   int64_t row_begin = int64_t(p) * a.rows_per_part;
   const int64_t row_end = min(a.N, row_begin + a.rows_per_part);
   // evaluation mode: bins live where the key buffers would be; tiles whose rows are all <= the first query are skipped
+  // Density bins are 16-bit, two per word (half the shared memory -> two CTAs per SM); they are flushed to the 64-bit
+  // global bins every kEvalFlushTiles tiles, before any of them can reach 2^16 (a tile adds at most 128 * TQ to a bin).
   uint32_t* ev_hist = reinterpret_cast<uint32_t*>(smem + kScanStages * STAGE_BYTES);
-  uint32_t* ev_thr = ev_hist + kEvalMetrics * 4 * (KIND == K_EVAL ? a.nbins : 0);
-  double* ev_thresholds = reinterpret_cast<double*>(ev_thr + kEvalMetrics * 2 * ((KIND == K_EVAL ? a.nthr : 0) + 1) + 2);
+  const int ev_hist_words = KIND == K_EVAL ? eval_hist_words(a.nbins) : 0;
+  uint32_t* ev_thr = ev_hist + ev_hist_words;
+  double* ev_thresholds = reinterpret_cast<double*>(
+      smem + kScanStages * STAGE_BYTES + round_up64((ev_hist_words + kEvalMetrics * 2 * ((KIND == K_EVAL ? a.nthr : 0) + 1)) * 4, 8));
+  constexpr int kEvalFlushTiles = 65535 / (kScanThreads * TQ);
+  auto flush_bins = [&]() {
+    __syncthreads();
+    const int nh = kEvalMetrics * 4 * a.nbins;
+    for (int i = tid; i < ev_hist_words; i += kScanThreads) {
+      const uint32_t w = ev_hist[i];
+      if (w) {
+        if (w & 0xffffu) atomicAdd(&a.hist[2 * i], (unsigned long long)(w & 0xffffu));
+        if ((w >> 16) && 2 * i + 1 < nh) atomicAdd(&a.hist[2 * i + 1], (unsigned long long)(w >> 16));
+        ev_hist[i] = 0;
+      }
+    }
+    __syncthreads();
+  };
   if constexpr (KIND == K_EVAL) {
     const int64_t sdiff = int64_t(g) * TQ - row_begin;
     if (sdiff >= kScanThreads - 1) row_begin += ((sdiff - (kScanThreads - 1)) / kScanThreads + 1) * kScanThreads;
     if (row_begin > row_end) row_begin = row_end;
-    const int nh = kEvalMetrics * 4 * a.nbins + kEvalMetrics * 2 * (a.nthr + 1);
+    const int nh = ev_hist_words + kEvalMetrics * 2 * (a.nthr + 1);
     for (int i = tid; i < nh; i += kScanThreads) ev_hist[i] = 0;
     for (int i = tid; i < a.nthr; i += kScanThreads) ev_thresholds[i] = a.thresholds[i];
   }
@@ -314,7 +332,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
             for (int m = 0; m < kEvalMetrics; ++m) {
               int bin = int(floorf((vals[m] - a.lo[m]) * a.inv_w[m]));
               bin = bin < 0 ? 0 : (bin >= a.nbins ? a.nbins - 1 : bin);
-              atomicAdd(&ev_hist[(m * 4 + rel) * a.nbins + bin], 1u);
+              const int slot = (m * 4 + rel) * a.nbins + bin;
+              atomicAdd(&ev_hist[slot >> 1], 1u << ((slot & 1) * 16));
               if (rel <= 1) {
                 // first threshold index with d <= threshold (thresholds ascending); nthr = none (mi_analysis.py:783-784)
                 const double dv = double(vals[m]);
@@ -344,6 +363,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
         for (int j = 0; j < NA; ++j) acc[t][j] = 0.f;
       }
       xsq = 0.f;
+      if constexpr (KIND == K_EVAL) {
+        if (tile % kEvalFlushTiles == 0) flush_bins();
+      }
       if (KIND != K_EVAL && topk_mode) {
         __syncthreads();
         for (int t = warp; t < TQ; t += kScanThreads / 32) {
@@ -359,8 +381,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
 
   if constexpr (KIND == K_EVAL) {
     __syncthreads();
-    const int nh = kEvalMetrics * 4 * a.nbins, nt = kEvalMetrics * 2 * (a.nthr + 1);
-    for (int i = tid; i < nh; i += kScanThreads) if (ev_hist[i]) atomicAdd(&a.hist[i], (unsigned long long)ev_hist[i]);
+    const int nt = kEvalMetrics * 2 * (a.nthr + 1);
+    flush_bins();
     for (int i = tid; i < nt; i += kScanThreads) if (ev_thr[i]) atomicAdd(&a.thr_counts[i], (unsigned long long)ev_thr[i]);
     return;
   }

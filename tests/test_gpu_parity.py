@@ -482,6 +482,32 @@ def test_allpairs_eval_counts(ops):
         assert hist[0, t].sum() == int((r == t).sum())
 
 
+def test_allpairs_eval_counter_flush_at_scale(ops):
+    """20k rows of ONE repeated vector pattern: every pair lands in the same few bins, so the 16-bit shared counters
+    would wrap without the periodic flush.  Totals and per-type totals are exact (size-independent properties)."""
+    N, D, nbins = 20000, 32, 64
+    base = synth.gaussian(4, D, 71)
+    X = base[np.arange(N) % 4]                                    # only 4 distinct rows -> <= 10 distinct distances
+    cat = np.arange(N) % 10
+    col = (np.arange(N) // 10) % 3
+    ranges = {m: (0.0, 4.0) for m in ("cosine_distance", "l1_distance", "l2_distance", "linf_distance", "magnitude_difference")}
+    hist, thr = ops.allpairs_eval(X, cat, col, ranges, nbins, np.linspace(0, 1, 100))
+    hist, thr = hist.cpu().numpy(), thr.cpu().numpy()
+    npairs = N * (N - 1) // 2
+    assert hist.sum(axis=(1, 2)).tolist() == [npairs] * 5
+    same_cat = sum(int(c) * (int(c) - 1) // 2 for c in np.bincount(cat))
+    key = cat * 3 + col
+    same_both = sum(int(c) * (int(c) - 1) // 2 for c in np.bincount(key))
+    same_col = sum(int(c) * (int(c) - 1) // 2 for c in np.bincount(col))
+    want = [same_both, same_cat - same_both, same_col - same_both, npairs - same_cat - same_col + same_both]
+    for m in range(5):
+        assert hist[m].sum(axis=1).tolist() == want, m
+        assert thr[m].sum(axis=1).tolist() == want[:2], m
+    # identical rows (i = j mod 4): distance exactly 0 -> bin 0 holds at least those pairs
+    ident = sum(int(c) * (int(c) - 1) // 2 for c in np.bincount(np.arange(N) % 4))
+    assert hist[1, :, 0].sum() >= ident and hist[3, :, 0].sum() >= ident
+
+
 # ------------------------------------------------------------------------------- explicit pair lists
 @pytest.mark.parametrize("D,dtype", [(512, "f32"), (64, "f32"), (7, "f32"), (513, "f32"), (512, "bf16"), (36, "bf16")])
 def test_pair_metrics_match_oracle(ops, D, dtype):
