@@ -59,6 +59,7 @@ __device__ __forceinline__ key128_t shfl_xor_key(key128_t v, int m) {
   return (key128_t(hi) << 64) | lo;
 }
 __device__ __forceinline__ uint64_t shfl_xor_key(uint64_t v, int m) { return shfl_xor_u64(v, m); }
+__device__ __forceinline__ uint32_t shfl_xor_key(uint32_t v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
 // Warp-wide ascending bitonic sort of 32*E keys held E per lane in blocked order
 // (global position of k[e] in lane l is l*E + e).  All 32 lanes must call.
@@ -91,6 +92,35 @@ __device__ __forceinline__ void warp_sort(K (&k)[E], int lane) {
             k[e] = sw ? b : a;
             k[e | stride] = sw ? a : b;
           }
+        }
+      }
+    }
+  }
+}
+
+// Final pass of the sort above on its own: `k` (32*E keys, blocked) holds a bitonic sequence, result ascending.
+template <int E, typename K>
+__device__ __forceinline__ void warp_bitonic_merge(K (&k)[E], int lane) {
+#pragma unroll
+  for (int stride = 16 * E; stride > 0; stride >>= 1) {
+    if (stride >= E) {
+      const int lstride = stride / E;
+      const bool lower = (lane & lstride) == 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const K other = shfl_xor_key(k[e], lstride);
+        const K mn = k[e] < other ? k[e] : other;
+        const K mx = k[e] < other ? other : k[e];
+        k[e] = lower ? mn : mx;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if ((e & stride) == 0) {
+          const K a = k[e], b = k[e | stride];
+          const bool sw = a > b;
+          k[e] = sw ? b : a;
+          k[e | stride] = sw ? a : b;
         }
       }
     }

@@ -43,8 +43,8 @@ constexpr int SMEM_A = MAX_KB * A_KB_BYTES;  // 128 KB
 constexpr int SMEM_B = B_STAGES * B_STAGE_BYTES;   // 96 KB
 constexpr int SMEM_SCALE = 2 * BN * 4;       // double-buffered per-column scale (rnorm / sqnorm)
 constexpr int SMEM_BARS = 192;
-constexpr int SMEM_CNT = 2 * BM * 2;        // per-query 16-bit candidate counters: front (warp 0 of the quarter) and back (warp 1)
-constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS + SMEM_CNT;   // 232,128 B <= 232,448
+constexpr int SMEM_CNT = 3 * BM * 2;        // per-query 16-bit counters: front (warp 0 of the quarter), back (warp 1), sorted prefix
+constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS + SMEM_CNT;   // 232,384 B <= 232,448
 constexpr int THREADS = 384;           // 4 control warps + 8 epilogue warps (two per TMEM lane quarter)
 constexpr int TMEM_COLS = 512;
 
@@ -66,6 +66,7 @@ struct Args {
   uint64_t* cand;        // [gridDim.x][128][cap]
   uint64_t* partial;     // [nq][P][kp]
   uint32_t* thr_g;       // [num_qtiles*128] best published k'-th rank value per query (ordered bits), 0xffffffff = none
+  uint32_t* lvl;         // [num_qtiles*128][kLevels][P] per-partition order statistics (see publish_levels), or nullptr
   unsigned long long* dbg;   // optional [gridDim.x][16] cycle counters (B200IR_GEMM_DEBUG=1), else nullptr
   int opt;               // experiment switches (B200IR_GEMM_OPT): bit 0 = L2 prefetch of the tile two ahead
 };
@@ -198,9 +199,51 @@ __device__ __forceinline__ void import_threshold(const uint32_t* thr_g_q, float&
 // quarter): sort, keep the best kp, publish the k'-th rank value.  Counters live in shared memory (`cnt_q`, one
 // per row of the quarter) because two epilogue warps append to the same list.  If `out` is set the sorted list
 // goes to the unit's output slot instead of back to the scratch list.
+// Threshold sharing between the units (database partitions) of one query.  A unit publishes, for levels j = 0..3, the
+// rank value of its ceil(kp / 2^j)-th best candidate so far (a statement "this partition holds that many rows at least
+// this good", which only gets stronger with time).  If 2^j different partitions each hold ceil(kp / 2^j) rows at least
+// as good as t, the database holds kp of them, so the 2^j-th best published level-j value is a valid threshold for
+// every unit of the query.  Level 0 alone (the best k'-th value of any single partition) is what a per-unit list can
+// give; the deeper levels make the threshold track the union of the partitions seen so far instead of one of them.
+constexpr int kLevels = 4;
+template <int E>
+__device__ __forceinline__ void publish_levels(const uint64_t (&r)[E], int n, int kp, int lane, uint32_t* thr_g_q, uint32_t* lvl_q,
+                                               int p, int P) {
+  uint32_t mine[kLevels];
+#pragma unroll
+  for (int j = 0; j < kLevels; ++j) {
+    const int m = (kp + (1 << j) - 1) >> j;
+    const int src_lane = (m - 1) / E, src_e = (m - 1) % E;
+    uint32_t hi = 0xffffffffu;
+#pragma unroll
+    for (int e = 0; e < E; ++e) if (e == src_e) hi = uint32_t(r[e] >> 32);
+    hi = __shfl_sync(0xffffffffu, hi, src_lane);
+    mine[j] = n >= m ? hi : 0xffffffffu;
+  }
+  if (lvl_q == nullptr) {                                     // more partitions than lanes: level 0 only
+    if (lane == 0 && mine[0] != 0xffffffffu) atomicMin(thr_g_q, mine[0]);
+    return;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < kLevels; ++j)
+      if (mine[j] != 0xffffffffu) *reinterpret_cast<volatile uint32_t*>(lvl_q + j * P + p) = mine[j];
+  }
+  __syncwarp();
+  uint32_t best = 0xffffffffu;
+#pragma unroll
+  for (int j = 0; j < kLevels; ++j) {
+    uint32_t x[1] = {lane < P ? *reinterpret_cast<const volatile uint32_t*>(lvl_q + j * P + lane) : 0xffffffffu};
+    warp_sort<1>(x, lane);                                    // ascending: lane i holds the (i+1)-th best published value
+    best = min(best, __shfl_sync(0xffffffffu, x[0], (1 << j) - 1));
+  }
+  if (lane == 0 && best != 0xffffffffu) atomicMin(thr_g_q, best);
+}
+
 template <int E>
 __device__ __noinline__ void compact_one(uint64_t* list, int cap, int kp, int n0, int n1, unsigned short* cnt_front,
-                                         unsigned short* cnt_back, int lane, uint64_t* dst, uint32_t* thr_g_q) {
+                                         unsigned short* cnt_back, unsigned short* srt, int lane, uint64_t* dst,
+                                         uint32_t* thr_g_q, uint32_t* lvl_q, int p, int P) {
   // the list is filled from both ends: warp 0 of the quarter appends at [0, n0), warp 1 at (cap - n1, cap]
   const int n = n0 + n1;
   uint64_t r[E];
@@ -216,18 +259,50 @@ __device__ __noinline__ void compact_one(uint64_t* list, int cap, int kp, int n0
     const int i = lane * E + e;
     if (i < kp) out[i] = r[e];
   }
-  if (dst == nullptr) {
-    const int src_lane = (kp - 1) / E, src_e = (kp - 1) % E;
-    uint64_t kth = kKeyInf;
-#pragma unroll
-    for (int e = 0; e < E; ++e) if (e == src_e) kth = r[e];
-    kth = shfl_u64(kth, src_lane);
-    if (lane == 0) {
-      *cnt_front = (unsigned short)(n < kp ? n : kp);   // the compacted list lives at the front
-      *cnt_back = 0;
-      if (n >= kp) atomicMin(thr_g_q, uint32_t(kth >> 32));
-    }
+  if (dst == nullptr && lane == 0) {
+    *cnt_front = (unsigned short)(n < kp ? n : kp);   // the compacted list lives at the front, sorted
+    *cnt_back = 0;
+    *srt = *cnt_front;
   }
+  publish_levels<E>(r, n, kp, lane, thr_g_q, lvl_q, p, P);
+  __syncwarp();
+}
+
+// Incremental compaction: the first `s` entries of the list are the sorted survivors of the previous compaction, so
+// only the h <= 32*E entries appended since then are sorted; the best 32*E of both come out of one bitonic merge
+// (C[i] = min(old[i], new[32E-1-i]) is bitonic and holds the 32E smallest).  Needs s <= 32*E and kp <= 32*E.
+template <int E>
+__device__ __noinline__ void compact_merge(uint64_t* list, int cap, int kp, int s, int n0, int n1, unsigned short* cnt_front,
+                                           unsigned short* cnt_back, unsigned short* srt, int lane, uint64_t* dst,
+                                           uint32_t* thr_g_q, uint32_t* lvl_q, int p, int P) {
+  const int hf = n0 - s, h = hf + n1, n = n0 + n1;
+  uint64_t rn[E], r[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    rn[e] = i < hf ? list[s + i] : (i < h ? list[cap - 1 - (i - hf)] : kKeyInf);
+  }
+  warp_sort<E>(rn, lane);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    const uint64_t old = i < s ? list[i] : kKeyInf;
+    const uint64_t rev = shfl_u64(rn[E - 1 - e], 31 - lane);       // new[32E - 1 - i]
+    r[e] = old < rev ? old : rev;
+  }
+  warp_bitonic_merge<E>(r, lane);
+  uint64_t* out = dst ? dst : list;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    if (i < kp) out[i] = r[e];
+  }
+  if (dst == nullptr && lane == 0) {
+    *cnt_front = (unsigned short)(n < kp ? n : kp);
+    *cnt_back = 0;
+    *srt = *cnt_front;
+  }
+  publish_levels<E>(r, n, kp, lane, thr_g_q, lvl_q, p, P);
   __syncwarp();
 }
 
@@ -235,7 +310,8 @@ __device__ __noinline__ void compact_one(uint64_t* list, int cap, int kp, int n0
 // quarter): sort, keep the best kp, publish the k'-th rank value.  The sorter width follows the list length.
 // If `out` is set the sorted list goes to the unit's output slot instead of back to the scratch list.
 __device__ __forceinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp, unsigned short* cnt_q, uint32_t mask, int lane,
-                                             uint64_t* out, int64_t out_stride, int valid_lanes, uint32_t* thr_g_warp) {
+                                             uint64_t* out, int64_t out_stride, int valid_lanes, uint32_t* thr_g_warp,
+                                             uint32_t* lvl_warp, int p, int P) {
   while (mask) {
     const int L = __ffs(mask) - 1;
     mask &= mask - 1;
@@ -246,8 +322,14 @@ __device__ __forceinline__ void warp_compact(uint64_t* warp_lists, int cap, int 
       if (L >= valid_lanes) continue;
       dst = out + int64_t(L) * out_stride;
     }
-    if (n0 + n1 <= 256) compact_one<8>(list, cap, kp, n0, n1, cnt_q + L, cnt_q + 32 + L, lane, dst, thr_g_warp + L);
-    else compact_one<16>(list, cap, kp, n0, n1, cnt_q + L, cnt_q + 32 + L, lane, dst, thr_g_warp + L);
+    uint32_t* lvl_q = lvl_warp ? lvl_warp + size_t(L) * kLevels * P : nullptr;
+    const int s = cnt_q[64 + L];                               // sorted prefix left by the previous compaction
+    const int h = n0 + n1 - s;
+    unsigned short *cf = cnt_q + L, *cb = cnt_q + 32 + L, *srt = cnt_q + 64 + L;
+    if (s > 0 && h <= 128 && kp <= 128) compact_merge<4>(list, cap, kp, s, n0, n1, cf, cb, srt, lane, dst, thr_g_warp + L, lvl_q, p, P);
+    else if (s > 0 && h <= 256) compact_merge<8>(list, cap, kp, s, n0, n1, cf, cb, srt, lane, dst, thr_g_warp + L, lvl_q, p, P);
+    else if (n0 + n1 <= 256) compact_one<8>(list, cap, kp, n0, n1, cf, cb, srt, lane, dst, thr_g_warp + L, lvl_q, p, P);
+    else compact_one<16>(list, cap, kp, n0, n1, cf, cb, srt, lane, dst, thr_g_warp + L, lvl_q, p, P);
   }
 }
 
@@ -444,7 +526,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
     uint64_t* warp_lists = a.cand + (size_t(blockIdx.x) * BM + quarter * 32) * a.cap;
     uint64_t* mylist = warp_lists + size_t(lane) * a.cap;
-    unsigned short* cnt_q = cnt_s + quarter * 64;          // [32 front counts | 32 back counts]
+    unsigned short* cnt_q = cnt_s + quarter * 96;          // [32 front counts | 32 back counts | 32 sorted-prefix lengths]
     volatile unsigned short* mycnt = cnt_q + half * 32 + lane;
     const int64_t lstep = half ? -1 : 1;                   // warp 0 fills the list upwards from 0, warp 1 downwards from cap-1
     uint64_t* const lbase = half ? mylist + a.cap - 1 : mylist;
@@ -457,6 +539,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float thr = 0.f;
     int cnt = 0;
     uint32_t* thr_g_warp = a.thr_g;
+    uint32_t* lvl_warp = nullptr;
+    int cur_p = 0;
     // publish my end's counter, meet the partner warp, compact every list longer than `limit` (lists split between
     // the two warps), pick up the new thresholds
     auto check_and_compact = [&](int limit, long long& tcomp) {
@@ -467,7 +551,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (full) {
         const long long tc0 = dbg_me ? clock64() : 0ll;
         const uint32_t mine = alternate_bits(full, half);
-        warp_compact(warp_lists, a.cap, a.kp, cnt_q, mine, lane, nullptr, 0, 32, thr_g_warp);
+        warp_compact(warp_lists, a.cap, a.kp, cnt_q, mine, lane, nullptr, 0, 32, thr_g_warp, lvl_warp, cur_p, a.P);
         pair_sync();
         if ((full >> lane) & 1) {
           cnt = int(*mycnt);                                                // kp (or fewer) at the front, 0 at the back
@@ -478,16 +562,21 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     };
     uint32_t titer = 0;
+    int dbg_round = -1;
     for (int unit = cluster_id; unit < num_units; unit += nclusters) {
+      ++dbg_round;
       const int qt = (unit % a.num_qgroups) * NCTA + int(rank), p = unit / a.num_qgroups;
       const int q = qt * BM + row;
       thr = q < a.nq ? -INFINITY : INFINITY;                   // padding rows of the last query tile accept nothing
       cnt = 0;                                                 // my end of the list (register; published at every barrier)
       *mycnt = 0;
+      if (half == 0) cnt_q[64 + lane] = 0;                     // nothing sorted yet
       pair_sync();
       const int tile0 = p * a.tiles_per_part;
       const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
       thr_g_warp = a.thr_g + qt * BM + quarter * 32;
+      lvl_warp = a.lvl ? a.lvl + size_t(qt * BM + quarter * 32) * kLevels * a.P : nullptr;
+      cur_p = p;
       import_threshold(thr_g_warp + lane, thr);
       for (int t = tile0; t < tile1; ++t, ++titer) {
         const int buf = titer & 1;
@@ -532,6 +621,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             gm[g8] = fmax3(fmax3(w[0], w[1], w[2]), fmax3(w[3], w[4], w[5]), fmaxf(w[6], w[7]));
           }
           const float mx = fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]);
+          if (a.dbg && warp == 4) {                                // debug build-in: how often a warp leaves the clean path
+            const bool any = __any_sync(0xffffffffu, mx > thr);
+            if (lane == 0 && any) a.dbg[blockIdx.x * 16 + (dbg_round == 0 ? 11 : 14)] += 1;
+          }
           if (mx > thr) {
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
@@ -574,7 +667,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (valid > 0) {
         uint64_t* out = a.partial + (int64_t(q0) * a.P + p) * a.kp;
         const uint32_t mine = half ? 0xffff0000u : 0x0000ffffu;
-        warp_compact(warp_lists, a.cap, a.kp, cnt_q, mine, lane, out, int64_t(a.P) * a.kp, valid, thr_g_warp);
+        warp_compact(warp_lists, a.cap, a.kp, cnt_q, mine, lane, out, int64_t(a.P) * a.kp, valid, thr_g_warp, lvl_warp, cur_p, a.P);
       }
       pair_sync();                                             // lists and counters may be reused by the next unit
       if (dbg_me) a.dbg[blockIdx.x * 16 + 10] += (unsigned long long)(clock64() - te0);
@@ -763,7 +856,7 @@ static bool encode_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, i
 
 struct Plan {
   int num_qtiles, num_qgroups, ncta, total_tiles, P, tiles_per_part, kp, cap, grid, num_kb;
-  size_t off_scale, off_thr, off_cand, off_partial, total_bytes;
+  size_t off_scale, off_thr, off_lvl, off_cand, off_partial, total_bytes;
 };
 
 static int num_sms() {
@@ -816,6 +909,7 @@ static Plan make_plan(int64_t nq, int64_t N, int D, int k, int flags, int sms) {
   size_t off = 0;
   pl.off_scale = off; off += round_up64(size_t(pl.total_tiles) * BN * 4, 256);
   pl.off_thr = off; off += round_up64(size_t(pl.num_qgroups) * pl.ncta * BM * 4, 256);
+  pl.off_lvl = off; off += pl.P <= 32 ? round_up64(size_t(pl.num_qgroups) * pl.ncta * BM * kLevels * pl.P * 4, 256) : 0;
   pl.off_cand = off; off += round_up64(size_t(pl.grid) * BM * pl.cap * 8, 256);
   pl.off_partial = off; off += round_up64(size_t(nq) * pl.P * pl.kp * 8, 256);
   pl.total_bytes = off;
@@ -858,7 +952,7 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
     ProfileScope ps(PT_PREP, st);
     const int64_t N_pad = int64_t(pl.total_tiles) * BN;
     row_scale_kernel<<<unsigned(ceil_div64(N_pad, 8)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(X), N, N_pad, D, mode == MODE_L2 ? 1 : 0, scale);
-    cudaError_t em = cudaMemsetAsync(ws + pl.off_thr, 0xff, size_t(pl.num_qgroups) * pl.ncta * BM * 4, st);
+    cudaError_t em = cudaMemsetAsync(ws + pl.off_thr, 0xff, pl.off_cand - pl.off_thr, st);      // thresholds + level slots
     if (em != cudaSuccess) return int(em);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return int(e);
@@ -870,6 +964,8 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
   a.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
   a.partial = reinterpret_cast<uint64_t*>(ws + pl.off_partial);
   a.thr_g = reinterpret_cast<uint32_t*>(ws + pl.off_thr);
+  static const int opt_env = getenv("B200IR_GEMM_OPT") ? atoi(getenv("B200IR_GEMM_OPT")) : 0;
+  a.lvl = (pl.P <= 32 && !(opt_env & 2)) ? reinterpret_cast<uint32_t*>(ws + pl.off_lvl) : nullptr;   // bit 1: level 0 only (A/B)
   static const bool dbg_on = getenv("B200IR_GEMM_DEBUG") != nullptr;
   static const int opt_flags = getenv("B200IR_GEMM_OPT") ? atoi(getenv("B200IR_GEMM_OPT")) : 0;
   a.opt = opt_flags;
@@ -917,8 +1013,8 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
     cudaStreamSynchronize(st);
     cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
     static const char* names[16] = {"prod_wait_Bempty", "prod_wait_Aempty", "prod_wait_Tempty", "mma_wait_Bfull", "mma_wait_Tempty",
-                                    "mma_wait_Afull", "mma_issue", "epi_wait_full", "epi_elements", "epi_compact", "epi_unit_end", "-",
-                                    "epi_compactions(w0)", "epi_tiles", "-", "-"};
+                                    "mma_wait_Afull", "mma_issue", "epi_wait_full", "epi_elements", "epi_compact", "epi_unit_end", "slow_visits_round0(w4)",
+                                    "epi_compactions(w0)", "epi_tiles", "slow_visits_later(w4)", "-"};
     fprintf(stderr, "[b200ir gemm debug] grid=%d ncta=%d P=%d tiles/part=%d kp=%d cap=%d (mean cycles per CTA)\n", pl.grid, pl.ncta, pl.P, pl.tiles_per_part, pl.kp, pl.cap);
     for (int sidx = 0; sidx < 16; ++sidx) {
       if (names[sidx][0] == '-') continue;
