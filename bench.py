@@ -47,7 +47,7 @@ def peaks():
 class ClockSampler:
     """Samples SM clock + throttle reasons during the timed region (NVML, else nvidia-smi)."""
 
-    def __init__(self, index=0, period=0.1):
+    def __init__(self, index=0, period=0.02):
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
@@ -609,7 +609,7 @@ def run_config4(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline")
