@@ -381,6 +381,22 @@ def run_headline(args):
 
 
 # ------------------------------------------------------------------------------------ other rows
+def side_cpu_baseline(kind, unit, fn, units_per_call, sample, budget_s=6.0):
+    """Bounded CPU leg of a side workload: the oracle (NumPy port of the reference arithmetic) on a small sample of the
+    same synthetic input, repeated until ~budget_s of CPU time is spent."""
+    fn()
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        fn()
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 50:
+            break
+    return {"value": n * units_per_call / dt, "unit": unit, "cores": 1 if kind == "loop" else os.cpu_count(), "kind": "port",
+            "sample": f"{sample}, {n} repeats, {dt:.1f} s"}
+
+
 def run_side(args):
     """Secondary s8(d) workloads (single GPU): HBM-bound scans, exact fp32 L2, histograms."""
     import ctypes
@@ -428,6 +444,13 @@ def run_side(args):
         ms, kms, launches, clocks = time_fn(lambda: ops.topk(Q, X, metric, k), 1)
         bytes_alg = N * D * 4
         ach = bytes_alg / (kms * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu:
+            from oracle import search as OS
+            ns = min(N, 100_000)
+            Xs, Qs = X[:ns].cpu().numpy(), Q.cpu().numpy()
+            cpu = side_cpu_baseline("blas", "queries/s", lambda: OS.topk_search(Qs, Xs, metric, k, dtype=np.float32),
+                                    nq * ns / N, f"{nq} queries vs the first {ns} rows (NumPy port, scaled linearly to {N} rows)")
         line = {"metric": f"queries/sec ({metric} top-{k}, {N}x{D} fp32 DB, {nq}-query batch)", "value": nq / (ms * 1e-3),
                 "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                 "higher_is_better": True, "dtype": "f32", "data": "synthetic relu(N(0,1))",
@@ -435,7 +458,7 @@ def run_side(args):
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "scan_topk", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel_ms": kms,
-                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}}
+                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}, "cpu_baseline": cpu}
         print(json.dumps(line))
     elif w == "histogram":
         B = args.rows or 8192
@@ -445,6 +468,11 @@ def run_side(args):
         ms, kms, launches, clocks = time_fn(lambda: ops.histogram(imgs, cs), 6)
         bytes_alg = B * (224 * 224 * 3 + 512 * 4)
         ach = bytes_alg / (kms * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu:
+            from oracle import histogram as OH
+            hs = imgs[:64].cpu().numpy()
+            cpu = side_cpu_baseline("numpy", "images/s", lambda: OH.histogram(hs, cs), 64, f"64 images, NumPy bincount port ({cs})")
         line = {"metric": f"images/sec (512-bin {cs} histogram, 224x224x3 uint8)", "value": B / (ms * 1e-3), "unit": "images/s",
                 "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
                 "dtype": "u8", "data": "synthetic uniform pixels",
@@ -452,7 +480,7 @@ def run_side(args):
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "histogram", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel_ms": kms,
-                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}}
+                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}, "cpu_baseline": cpu}
         print(json.dumps(line))
     elif w == "config5":
         # BASELINE configs[4]: all-pairs evaluation (5 metrics, 4 relationship types, density histograms + PR counts)
@@ -466,6 +494,15 @@ def run_side(args):
                   "linf_distance": (0.0, 8.0), "magnitude_difference": (0.0, 6.0)}
         ms, kms, launches, clocks = time_fn(lambda: ops.allpairs_eval(X, cat, col, ranges, 1024), 1)
         pairs = N * (N - 1) / 2
+        cpu = None
+        if not args.no_cpu:
+            from oracle import evaluation as E
+            ns = 1500
+            Xs, cs_, ks_ = X[:ns].cpu().numpy(), cat[:ns].cpu().numpy(), col[:ns].cpu().numpy()
+            thr_np = np.linspace(0, 1, 100)
+            cpu = side_cpu_baseline("blas", "pairs/s",
+                                    lambda: E.bin_counts(E.metric_matrices(Xs, np.float32), E.relationship(cs_, ks_), ranges, 1024, thr_np),
+                                    ns * (ns - 1) / 2, f"all pairs of the first {ns} rows, vectorised NumPy port of the five metrics + binning")
         lane_ops = pairs * D * 5.25                              # dot, |d|, d^2, max|d| + shared x^2: instructions per element pair
         peak = 148 * 128 * 1.965e9
         line = {"metric": f"pairs/sec (all-pairs evaluation, {N}x{N}, D={D}, 5 metrics)", "value": pairs / (ms * 1e-3), "unit": "pairs/s",
@@ -474,7 +511,8 @@ def run_side(args):
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "fp32-alu", "kernel": "scan_topk<K_EVAL>", "achieved": lane_ops / (kms * 1e-3) / 1e12,
                              "peak": peak / 1e12, "unit": "T lane-instr/s", "frac": lane_ops / (kms * 1e-3) / peak, "kernel_ms": kms,
-                             "note": "CUDA-core bound: 5.25 fp32 lane-instructions per element pair; peak = 148 SMs x 128 lanes x 1.965 GHz"}}
+                             "note": "CUDA-core bound: 5.25 fp32 lane-instructions per element pair; peak = 148 SMs x 128 lanes x 1.965 GHz"},
+                "cpu_baseline": cpu}
         print(json.dumps(line))
     elif w == "resize":
         # image front-end: PIL-exact bicubic resize (shorter edge -> 224) + centre crop, then the 512-bin histogram
@@ -489,6 +527,23 @@ def run_side(args):
         cols = min(W, int((left + 224) * scale + 2 * scale + 1)) - max(0, int(left * scale - 2 * scale))
         bytes_alg = B * (H * cols * 3 + 224 * 224 * 3)            # source window the crop depends on + cropped output
         ach = bytes_alg / (kms * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu:
+            try:
+                from PIL import Image
+                from oracle import histogram as OH
+                hs = imgs[:32].cpu().numpy()
+
+                def pil_front_end():
+                    out = []
+                    for im in hs:
+                        r = np.asarray(Image.fromarray(im).resize((rw, rh), resample=Image.BICUBIC))
+                        out.append(r[(rh - 224) // 2:(rh - 224) // 2 + 224, left:left + 224])
+                    return OH.histogram(np.stack(out), "rgb")
+                cpu = side_cpu_baseline("loop", "images/s", pil_front_end, 32, "32 images, PIL resize(BICUBIC) + crop (the reference's "
+                                        "processor front-end) + NumPy histogram, one core")
+            except ImportError:
+                cpu = None
         line = {"metric": f"images/sec (bicubic resize {H}x{W} -> 224 crop + 512-bin histogram)", "value": B / (ms * 1e-3),
                 "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                 "higher_is_better": True, "dtype": "u8", "data": "synthetic uniform pixels",
@@ -496,7 +551,7 @@ def run_side(args):
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "resize_crop", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel_ms": kms,
-                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}}
+                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}, "cpu_baseline": cpu}
         print(json.dumps(line))
     elif w == "pairs":
         # explicit pair lists (mi_analysis.py:256-297): P random pairs over an N x D fp32 store, seven values per pair
@@ -510,6 +565,13 @@ def run_side(args):
         ms, kms, launches, clocks = time_fn(lambda: ops.pair_metrics(X, None, ia, ib), 7)
         bytes_alg = P * (2 * D * 4 + 16 + 28)
         ach = bytes_alg / (kms * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu:
+            from oracle import metrics as OM
+            ns = 2000
+            Xa, Xb = X[ia[:ns]].cpu().numpy(), X[ib[:ns]].cpu().numpy()
+            cpu = side_cpu_baseline("loop", "pairs/s", lambda: [OM.get_all_metrics(a, b) for a, b in zip(Xa, Xb)], ns,
+                                    f"{ns} pairs, get_all_metrics per pair (the reference loop mi_analysis.py:277-291), one core")
         line = {"metric": f"pairs/sec (get_all_metrics over an explicit pair list, {N}x{D} fp32 store)", "value": P / (ms * 1e-3),
                 "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                 "higher_is_better": True, "dtype": "f32", "data": "synthetic N(0,1), uniform random pairs",
@@ -517,7 +579,7 @@ def run_side(args):
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "pair_metrics", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel_ms": kms,
-                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}}
+                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}, "cpu_baseline": cpu}
         print(json.dumps(line))
     elif w == "config1":
         def palette_images(b, seed):
