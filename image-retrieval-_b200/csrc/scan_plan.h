@@ -8,7 +8,7 @@ namespace b200ir {
 enum ScanKind { K_L1 = 0, K_L2 = 1, K_LINF = 2, K_DOT = 3, K_MULTI = 4, K_EVAL = 5 };
 
 constexpr int kScanThreads = 128;   // == rows per tile (one row per thread)
-constexpr int kScanStages = 3;
+constexpr int kScanStages = 2;
 constexpr int kRowChunkBytes = 128; // bytes of one row staged per pipeline step
 
 __host__ __device__ inline int scan_kind_of(int metric) {
