@@ -9,6 +9,7 @@ enum ScanKind { K_L1 = 0, K_L2 = 1, K_LINF = 2, K_DOT = 3, K_MULTI = 4, K_EVAL =
 
 constexpr int kScanThreads = 128;   // == rows per tile (one row per thread)
 constexpr int kScanStages = 2;
+constexpr int kEvalStages = 1;     // all-pairs evaluation: the bins take 40 KB, a one-stage ring lets three CTAs share an SM
 constexpr int kRowChunkBytes = 128; // bytes of one row staged per pipeline step
 
 __host__ __device__ inline int scan_kind_of(int metric) {
@@ -60,7 +61,7 @@ inline size_t scan_stage_bytes(int TQ, int DKE) {
 // density bins in shared memory: 16-bit counters, two per 32-bit word
 __host__ __device__ inline int eval_hist_words(int nbins) { return (kEvalMetrics * 4 * nbins + 1) / 2; }
 inline size_t eval_smem_bytes(int nbins, int nthr) {
-  return size_t(kScanStages) * scan_stage_bytes(kEvalTQ, 32) +
+  return size_t(kEvalStages) * scan_stage_bytes(kEvalTQ, 32) +
          size_t(eval_hist_words(nbins)) * 4 + size_t(kEvalMetrics) * 2 * (nthr + 1) * 4 + size_t(nthr) * 8 + 16 + 64;
 }
 cudaError_t launch_scan_eval_f32(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, size_t smem, cudaStream_t st);

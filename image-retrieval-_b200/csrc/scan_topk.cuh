@@ -103,10 +103,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
   constexpr int XT_BYTES = kScanThreads * kRowChunkBytes;  // 16 KB database tile per stage
   constexpr int QC_BYTES = TQ * DKE * 4;                   // fp32 query chunk per stage
   constexpr int STAGE_BYTES = XT_BYTES + (QC_BYTES + 1023) / 1024 * 1024;   // tiles stay 1024-byte aligned (TMA swizzle)
+  constexpr int NST = KIND == K_EVAL ? kEvalStages : kScanStages;           // ring depth
 
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* stage_base = smem;
-  uint64_t* keys_s = reinterpret_cast<uint64_t*>(smem + kScanStages * STAGE_BYTES);
+  uint64_t* keys_s = reinterpret_cast<uint64_t*>(smem + NST * STAGE_BYTES);
   uint64_t* thr_s = keys_s + size_t(TQ) * a.sortn;
   int* cnt_s = reinterpret_cast<int*>(thr_s + TQ);
 
@@ -118,11 +119,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
   // evaluation mode: bins live where the key buffers would be; tiles whose rows are all <= the first query are skipped
   // Density bins are 16-bit, two per word (half the shared memory -> two CTAs per SM); they are flushed to the 64-bit
   // global bins every kEvalFlushTiles tiles, before any of them can reach 2^16 (a tile adds at most 128 * TQ to a bin).
-  uint32_t* ev_hist = reinterpret_cast<uint32_t*>(smem + kScanStages * STAGE_BYTES);
+  uint32_t* ev_hist = reinterpret_cast<uint32_t*>(smem + NST * STAGE_BYTES);
   const int ev_hist_words = KIND == K_EVAL ? eval_hist_words(a.nbins) : 0;
   uint32_t* ev_thr = ev_hist + ev_hist_words;
   double* ev_thresholds = reinterpret_cast<double*>(
-      smem + kScanStages * STAGE_BYTES + round_up64((ev_hist_words + kEvalMetrics * 2 * ((KIND == K_EVAL ? a.nthr : 0) + 1)) * 4, 8));
+      smem + NST * STAGE_BYTES + round_up64((ev_hist_words + kEvalMetrics * 2 * ((KIND == K_EVAL ? a.nthr : 0) + 1)) * 4, 8));
   constexpr int kEvalFlushTiles = 65535 / (kScanThreads * TQ);
   auto flush_bins = [&]() {
     __syncthreads();
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
   if (a.use_tma) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     if (tid == 0) {
-      for (int s = 0; s < kScanStages; ++s) tma::mbar_init(full_bar0 + 8u * s, 1);
+      for (int s = 0; s < NST; ++s) tma::mbar_init(full_bar0 + 8u * s, 1);
       tma::mbar_fence_init();
       tma::prefetch_desc(&tmX);
       tma::prefetch_desc(&tmQ);
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
           tma::load_2d(sbu + XT_BYTES, &tmQ, bar, iss_chunk * DKE, g * TQ);
         }
         if (++iss_chunk == nchunks) { iss_chunk = 0; ++iss_tile; }
-        if (++iss_stage == kScanStages) iss_stage = 0;
+        if (++iss_stage == NST) iss_stage = 0;
       }
       return;
     }
@@ -228,13 +229,13 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
       static_assert(TQ * DKE / 4 <= kScanThreads, "query chunk must fit one cp.async per thread");
       if (tid < TQ * DKE / 4) cp_async_16(sbu + ld_qdst, ld_q + iss_chunk * DKE, 16);
       if (++iss_chunk == nchunks) { iss_chunk = 0; ++iss_tile; }
-      if (++iss_stage == kScanStages) iss_stage = 0;
+      if (++iss_stage == NST) iss_stage = 0;
     }
     cp_async_commit();
   };
 
 #pragma unroll
-  for (int s = 0; s < kScanStages - 1; ++s) issue();
+  for (int s = 0; s < NST - 1; ++s) issue();
 
   float acc[TQ][NA];
   float xsq = 0.f;
@@ -252,15 +253,20 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
     if (a.use_tma) {
       __syncthreads();                       // everyone is done with the stage that is refilled next
       issue();
-      tma::mbar_wait(full_bar0 + 8u * stage, (it / kScanStages) & 1);
-    } else {
-      cp_async_wait<kScanStages - 2>();
+      tma::mbar_wait(full_bar0 + 8u * stage, (it / NST) & 1);
+    } else if constexpr (NST >= 2) {
+      cp_async_wait<(NST >= 2 ? NST - 2 : 0)>();
       __syncthreads();
       issue();
+    } else {
+      __syncthreads();                       // one-stage ring: refill, then wait for this very chunk
+      issue();
+      cp_async_wait<0>();
+      __syncthreads();
     }
 
     const unsigned char* sb = stage_base + stage * STAGE_BYTES;
-    if (++stage == kScanStages) stage = 0;
+    if (++stage == NST) stage = 0;
     const unsigned char* xrow = sb + tid * kRowChunkBytes;
     const float* qs = reinterpret_cast<const float*>(sb + XT_BYTES);
 

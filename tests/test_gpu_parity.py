@@ -482,6 +482,25 @@ def test_allpairs_eval_counts(ops):
         assert hist[0, t].sum() == int((r == t).sum())
 
 
+@pytest.mark.parametrize("D", [33, 7, 100])
+def test_allpairs_eval_unaligned_rows(ops, D):
+    """Rows that are not 16-byte aligned take the cp.async / element-load ring (one stage deep in evaluation mode)."""
+    from oracle import evaluation as E
+    N, nbins = 300, 64
+    X = synth.gaussian(N, D, 80 + D)
+    cat, col = np.arange(N) % 7, (np.arange(N) // 7) % 3
+    ranges = {m: (0.0, 6.0) for m in E.METRICS}
+    thresholds = np.linspace(0, 1, 100)
+    hist, thr = ops.allpairs_eval(X, cat, col, ranges, nbins, thresholds)
+    hist, thr = hist.cpu().numpy(), thr.cpu().numpy()
+    names = {"cosine_distance": "cosine_distance", "l1_distance": "l1", "l2_distance": "l2", "linf_distance": "linf",
+             "magnitude_difference": "magnitude_difference"}
+    vals = {m: ops.pairwise(X, X, names[m]).cpu().numpy() for m in E.METRICS}
+    h2, t2 = E.bin_counts(vals, E.relationship(cat, col), ranges, nbins, thresholds)
+    assert hist.sum(axis=(1, 2)).tolist() == [N * (N - 1) // 2] * 5
+    assert np.abs(hist - h2).sum() <= 10 and np.abs(thr - t2).sum() <= 10
+
+
 def test_allpairs_eval_counter_flush_at_scale(ops):
     """20k rows of ONE repeated vector pattern: every pair lands in the same few bins, so the 16-bit shared counters
     would wrap without the periodic flush.  Totals and per-type totals are exact (size-independent properties)."""
