@@ -964,10 +964,11 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
   a.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
   a.partial = reinterpret_cast<uint64_t*>(ws + pl.off_partial);
   a.thr_g = reinterpret_cast<uint32_t*>(ws + pl.off_thr);
-  static const int opt_env = getenv("B200IR_GEMM_OPT") ? atoi(getenv("B200IR_GEMM_OPT")) : 0;
-  a.lvl = (pl.P <= 32 && !(opt_env & 2)) ? reinterpret_cast<uint32_t*>(ws + pl.off_lvl) : nullptr;   // bit 1: level 0 only (A/B)
-  static const bool dbg_on = getenv("B200IR_GEMM_DEBUG") != nullptr;
+  // measurement switches (same-box A/B runs): B200IR_GEMM_OPT bit 0 = L2 prefetch of the tile two ahead (off: 2 % slower),
+  // bit 1 = publish level 0 only (per-partition thresholds, the pre-"levels" behaviour); B200IR_GEMM_DEBUG = cycle counters
   static const int opt_flags = getenv("B200IR_GEMM_OPT") ? atoi(getenv("B200IR_GEMM_OPT")) : 0;
+  static const bool dbg_on = getenv("B200IR_GEMM_DEBUG") != nullptr;
+  a.lvl = (pl.P <= 32 && !(opt_flags & 2)) ? reinterpret_cast<uint32_t*>(ws + pl.off_lvl) : nullptr;
   a.opt = opt_flags;
   static unsigned long long* dbg_buf = nullptr;
   if (dbg_on) {
