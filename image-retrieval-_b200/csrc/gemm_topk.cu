@@ -32,21 +32,26 @@ namespace b200ir {
 namespace gemm {
 
 constexpr int BM = 128;            // queries per tile (UMMA M, TMEM lanes)
-constexpr int BN = 256;            // database rows per tile (UMMA N, TMEM columns per accumulator)
+#ifndef GEMM_BN
+#define GEMM_BN 256
+#endif
+constexpr int BN = GEMM_BN;        // database rows per tile (UMMA N, TMEM columns per accumulator)
 constexpr int BK = 64;             // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int MAX_KB = 8;          // D <= 512
-constexpr int B_STAGES = 3;
+constexpr int TMEM_COLS = 512;
+constexpr int NBUF = TMEM_COLS / BN;         // accumulators in flight (2 x 256 or 4 x 128 columns)
+constexpr int B_STAGES = BN == 256 ? 3 : 5;
 constexpr int A_KB_BYTES = BM * BK * 2;      // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int SMEM_A = MAX_KB * A_KB_BYTES;  // 128 KB
 constexpr int SMEM_B = B_STAGES * B_STAGE_BYTES;   // 96 KB
-constexpr int SMEM_SCALE = 2 * BN * 4;       // double-buffered per-column scale (rnorm / sqnorm)
-constexpr int SMEM_BARS = 192;
+constexpr int SMEM_SCALE = NBUF * BN * 4;    // per-column scale (rnorm / sqnorm), one buffer per accumulator
+constexpr int SMEM_BARS = BN == 256 ? 192 : 320;
 constexpr int SMEM_CNT = 3 * BM * 2;        // per-query 16-bit counters: front (warp 0 of the quarter), back (warp 1), sorted prefix
 constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS + SMEM_CNT;   // 232,384 B <= 232,448
 constexpr int THREADS = 384;           // 4 control warps + 8 epilogue warps (two per TMEM lane quarter)
-constexpr int TMEM_COLS = 512;
+static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 
 enum Mode { MODE_COS = 0, MODE_ABSCOS = 1, MODE_L2 = 2 };
 
@@ -376,7 +381,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sB = smem + SMEM_A;
   float* sScale = reinterpret_cast<float*>(smem + SMEM_A + SMEM_B);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_A + SMEM_B + SMEM_SCALE);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 10);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 2 + 4 * NBUF);
   unsigned short* cnt_s = reinterpret_cast<unsigned short*>(smem + SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS);
 
   const uint32_t bar0 = smem_u32(bars);
@@ -384,10 +389,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto B_EMPTY = [&](int s) { return bar0 + 8u * (NST + s); };
   const uint32_t A_FULL = bar0 + 8u * (2 * NST), A_EMPTY = bar0 + 8u * (2 * NST + 1);
   auto T_FULL = [&](int b) { return bar0 + 8u * (2 * NST + 2 + b); };
-  auto T_EMPTY = [&](int b) { return bar0 + 8u * (2 * NST + 4 + b); };     // local: this CTA's epilogue released buffer b
-  auto S_FULL = [&](int b) { return bar0 + 8u * (2 * NST + 6 + b); };
-  auto TE_MMA = [&](int b) { return bar0 + 8u * (2 * NST + 8 + b); };      // leader: every epilogue warp of the cluster released b
-  static_assert((2 * NST + 10) * 8 + 8 <= SMEM_BARS, "barrier area");
+  auto T_EMPTY = [&](int b) { return bar0 + 8u * (2 * NST + 2 + NBUF + b); };     // local: this CTA's epilogue released buffer b
+  auto S_FULL = [&](int b) { return bar0 + 8u * (2 * NST + 2 + 2 * NBUF + b); };
+  auto TE_MMA = [&](int b) { return bar0 + 8u * (2 * NST + 2 + 3 * NBUF + b); };  // leader: every epilogue warp of the cluster released b
+  static_assert((2 * NST + 2 + 4 * NBUF) * 8 + 8 <= SMEM_BARS, "barrier area");
   const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
   const int cluster_id = blockIdx.x / NCTA, nclusters = gridDim.x / NCTA;
 
@@ -404,7 +409,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < NST; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
     mbar_init(A_FULL, 1);
     mbar_init(A_EMPTY, 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NBUF; ++b) {
       mbar_init(T_FULL(b), 1); mbar_init(T_EMPTY(b), 8); mbar_init(S_FULL(b), 1); mbar_init(TE_MMA(b), 8 * NCTA);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -457,9 +462,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           // per-column scale of this tile: its buffer is free once the epilogue released accumulator `buf`
           // two tiles ago (already true by now in steady state: the MMAs of this tile are running)
-          const int buf = titer & 1;
+          const int buf = titer % NBUF;
           t0 = DBG_T0();
-          mbar_wait(T_EMPTY(buf), ((titer >> 1) & 1) ^ 1);
+          mbar_wait(T_EMPTY(buf), ((titer / NBUF) & 1) ^ 1);
           DBG_ADD(2, t0);
           mbar_expect_tx(S_FULL(buf), BN * 4);
           bulk_load_1d(smem_u32(sScale + buf * BN), a.colscale + int64_t(t) * BN, BN * 4, S_FULL(buf));
@@ -479,9 +484,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         DBG_ADD(5, t0);
         tc_fence_after();
         for (int t = tile0; t < tile1; ++t, ++titer) {
-          const int buf = titer & 1;
+          const int buf = titer % NBUF;
           t0 = DBG_T0();
-          mbar_wait(TE_MMA(buf), ((titer >> 1) & 1) ^ 1);      // every epilogue warp of the cluster drained this accumulator
+          mbar_wait(TE_MMA(buf), ((titer / NBUF) & 1) ^ 1);      // every epilogue warp of the cluster drained this accumulator
           DBG_ADD(4, t0);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + uint32_t(buf * BN);
@@ -579,7 +584,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       cur_p = p;
       import_threshold(thr_g_warp + lane, thr);
       for (int t = tile0; t < tile1; ++t, ++titer) {
-        const int buf = titer & 1;
+        const int buf = titer % NBUF;
         if (((t - tile0) & 7) == 7) import_threshold(thr_g_warp + lane, thr);      // other units' published thresholds
         long long tcomp = 0;
         if (tile_mode) {
@@ -589,8 +594,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (dbg_me) { a.dbg[blockIdx.x * 16 + 9] += (unsigned long long)tcomp; tcomp = 0; }
         }
         long long t0 = dbg_me ? clock64() : 0ll;
-        mbar_wait(S_FULL(buf), (titer >> 1) & 1);
-        mbar_wait(T_FULL(buf), (titer >> 1) & 1);
+        mbar_wait(S_FULL(buf), (titer / NBUF) & 1);
+        mbar_wait(T_FULL(buf), (titer / NBUF) & 1);
         if (dbg_me) { a.dbg[blockIdx.x * 16 + 7] += (unsigned long long)(clock64() - t0); t0 = clock64(); }
         tc_fence_after();
         const float* sc = sScale + buf * BN;
