@@ -597,10 +597,23 @@ def run_side(args):
             Qm = ops.counts_to_embedding(ops.histogram(qi))[0]
             return ops.topk(Qm, X, "l2", 10)
         ms, kms, launches, clocks = time_fn(fn, 1)
+        cpu = None
+        if not args.no_cpu:
+            from oracle import histogram as OH
+            from oracle import search as OS
+            qh, dh = qi[:100].cpu().numpy(), di[:1000].cpu().numpy()
+
+            def cpu_pass():
+                Xc = OH.histogram(dh, "rgb").astype(np.float32)
+                Qc = OH.histogram(qh, "rgb").astype(np.float32)
+                return OS.topk_search(Qc, Xc, "l2", 10, dtype=np.float32)
+            cpu = side_cpu_baseline("numpy", "queries/s", cpu_pass, 100, "100 query + 1000 database images (a tenth of config 1 on "
+                                    "both sides, same 10 database images per query: histogram port + NumPy L2 top-10)")
         line = {"metric": "queries/sec (config 1: histogram embeddings of 1k+10k images, L2 top-10 over 10kx512 fp32)",
                 "value": 1000 / (ms * 1e-3), "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": ms,
                 "higher_is_better": True, "dtype": "u8 -> f32", "data": "synthetic palette images",
-                "config": {"workload": "configs[0]"}, "gpu_launches": int(launches), "clocks": clocks, "scan_kernel_ms": kms}
+                "config": {"workload": "configs[0]"}, "gpu_launches": int(launches), "clocks": clocks, "scan_kernel_ms": kms,
+                "cpu_baseline": cpu}
         print(json.dumps(line))
     else:
         raise SystemExit(f"unknown workload {w}")
