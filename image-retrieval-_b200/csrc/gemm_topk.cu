@@ -76,8 +76,9 @@ struct Args {
   int opt;               // experiment switches (B200IR_GEMM_OPT): bit 0 = L2 prefetch of the tile two ahead
 };
 
-#define DBG_T0() (a.dbg ? clock64() : 0ll)
-#define DBG_ADD(slot, t0) do { if (a.dbg) a.dbg[blockIdx.x * 16 + (slot)] += (unsigned long long)(clock64() - (t0)); } while (0)
+#define DBG_ON (a.dbg && !(a.opt & 64))            /* B200IR_GEMM_OPT bit 6: keep only the per-round timers */
+#define DBG_T0() (DBG_ON ? clock64() : 0ll)
+#define DBG_ADD(slot, t0) do { if (DBG_ON) a.dbg[blockIdx.x * 16 + (slot)] += (unsigned long long)(clock64() - (t0)); } while (0)
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -479,6 +480,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int p = unit / a.num_qgroups;
         const int tile0 = p * a.tiles_per_part;
         const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
+        if (a.dbg) {                                             // MMA-issue time stamps per round: slot 15 = round 0, 11 = later
+          const long long now = clock64();
+          if (uiter == 1) a.dbg[blockIdx.x * 16 + 15] = (unsigned long long)(now - (long long)a.dbg[blockIdx.x * 16 + 14]);
+          if (uiter == 0) a.dbg[blockIdx.x * 16 + 14] = (unsigned long long)now;
+        }
         long long t0 = DBG_T0();
         mbar_wait(A_FULL, uiter & 1);
         DBG_ADD(5, t0);
@@ -515,6 +521,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if constexpr (NCTA == 2) tc_commit_2cta(T_FULL(buf)); else tc_commit(T_FULL(buf));    // accumulator complete -> epilogue
         }
         if constexpr (NCTA == 2) tc_commit_2cta(A_EMPTY); else tc_commit(A_EMPTY);
+        if (a.dbg && unit + nclusters >= num_units)              // total issue time of this cluster (slot 11)
+          a.dbg[blockIdx.x * 16 + 11] = (unsigned long long)(clock64() - (long long)a.dbg[blockIdx.x * 16 + 14]);
       }
     }
   } else if (warp >= 4) {
@@ -536,7 +544,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int64_t lstep = half ? -1 : 1;                   // warp 0 fills the list upwards from 0, warp 1 downwards from cap-1
     uint64_t* const lbase = half ? mylist + a.cap - 1 : mylist;
     const uint32_t tmem_lane = uint32_t(quarter * 32) << 16;
-    const bool dbg_me = a.dbg && warp == 4 && lane == 0;
+    const bool dbg_me = DBG_ON && warp == 4 && lane == 0;
     // tile mode: lists are checked once per tile and compacted when longer than tile_limit (<= 256 keys: the narrow
     // sorter is enough in the common case); a tile adds at most BN entries, so tile_limit + BN must fit the list
     const int tile_limit = max(a.kp + 64, 192);
@@ -626,10 +634,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             gm[g8] = fmax3(fmax3(w[0], w[1], w[2]), fmax3(w[3], w[4], w[5]), fmaxf(w[6], w[7]));
           }
           const float mx = fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]);
-          if (a.dbg && warp == 4) {                                // debug build-in: how often a warp leaves the clean path
-            const bool any = __any_sync(0xffffffffu, mx > thr);
-            if (lane == 0 && any) a.dbg[blockIdx.x * 16 + (dbg_round == 0 ? 11 : 14)] += 1;
-          }
           if (mx > thr) {
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
@@ -1019,8 +1023,8 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
     cudaStreamSynchronize(st);
     cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
     static const char* names[16] = {"prod_wait_Bempty", "prod_wait_Aempty", "prod_wait_Tempty", "mma_wait_Bfull", "mma_wait_Tempty",
-                                    "mma_wait_Afull", "mma_issue", "epi_wait_full", "epi_elements", "epi_compact", "epi_unit_end", "slow_visits_round0(w4)",
-                                    "epi_compactions(w0)", "epi_tiles", "slow_visits_later(w4)", "-"};
+                                    "mma_wait_Afull", "mma_issue", "epi_wait_full", "epi_elements", "epi_compact", "epi_unit_end", "mma_all_rounds",
+                                    "epi_compactions(w0)", "epi_tiles", "t_start", "mma_round0"};
     fprintf(stderr, "[b200ir gemm debug] grid=%d ncta=%d P=%d tiles/part=%d kp=%d cap=%d (mean cycles per CTA)\n", pl.grid, pl.ncta, pl.P, pl.tiles_per_part, pl.kp, pl.cap);
     for (int sidx = 0; sidx < 16; ++sidx) {
       if (names[sidx][0] == '-') continue;
