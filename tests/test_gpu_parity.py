@@ -273,6 +273,17 @@ def test_histogram_bit_exact(ops, cs, golden_dir):
     assert np.array_equal(ops.histogram(flat, cs).cpu().numpy().astype(np.uint32), OH.histogram(flat, cs))
 
 
+@pytest.mark.parametrize("cs", ["rgb", "hsv"])
+def test_histogram_every_colour(ops, cs):
+    """All 2^24 RGB colours, 4096 per image (so a mis-binned colour cannot hide behind another one): the kernel's integer
+    HSV conversion and binning agree with the oracle (itself checked against OpenCV on all colours) everywhere."""
+    c = np.arange(1 << 24, dtype=np.uint32)
+    imgs = np.stack([(c >> 16) & 255, (c >> 8) & 255, c & 255], axis=1).astype(np.uint8).reshape(4096, 64, 64, 3)
+    got = ops.histogram(imgs, cs).cpu().numpy().astype(np.uint32)
+    want = np.concatenate([OH.histogram(imgs[i:i + 512], cs) for i in range(0, 4096, 512)])
+    assert np.array_equal(got, want)
+
+
 def test_histogram_embedding(ops):
     imgs = synth.images_palette(6, 64, 64, 9)
     raw, unit, mag = ops.counts_to_embedding(ops.histogram(imgs))
