@@ -45,11 +45,11 @@ __global__ void __launch_bounds__(kHistThreads) histogram_kernel(const uint8_t* 
   uint32_t* myhist = hist[warp];
   int cur_bin = -1;
   uint32_t run = 0;
-  auto add_pixel = [&](int r, int g, int b) {
-    const int bin = HSV ? hsv_bin(r, g, b, s_sdiv, s_hdiv) : rgb_bin(r, g, b);
+  auto add_bin = [&](int bin) {
     if (bin == cur_bin) { ++run; }
     else { if (run) atomicAdd(&myhist[cur_bin], run); cur_bin = bin; run = 1; }
   };
+  auto add_pixel = [&](int r, int g, int b) { add_bin(HSV ? hsv_bin(r, g, b, s_sdiv, s_hdiv) : rgb_bin(r, g, b)); };
 
   if (vector_ok) {
     // 16 pixels = 48 bytes = three 128-bit loads per thread per step
@@ -65,10 +65,19 @@ __global__ void __launch_bounds__(kHistThreads) histogram_kernel(const uint8_t* 
 #pragma unroll
       for (int p = 0; p < 16; ++p) {
         const int b0 = p * 3, b1 = b0 + 1, b2 = b0 + 2;
-        const int r = int(__byte_perm(w[b0 >> 2], 0, 0x4440 | (b0 & 3)));      // one PRMT per byte
-        const int g = int(__byte_perm(w[b1 >> 2], 0, 0x4440 | (b1 & 3)));
-        const int bl = int(__byte_perm(w[b2 >> 2], 0, 0x4440 | (b2 & 3)));
-        add_pixel(r, g, bl);
+        if constexpr (HSV) {
+          const int r = int(__byte_perm(w[b0 >> 2], 0, 0x4440 | (b0 & 3)));      // one PRMT per byte
+          const int g = int(__byte_perm(w[b1 >> 2], 0, 0x4440 | (b1 & 3)));
+          const int bl = int(__byte_perm(w[b2 >> 2], 0, 0x4440 | (b2 & 3)));
+          add_pixel(r, g, bl);
+        } else {
+          // RGB bin straight from the packed pixel: align its three bytes to bits 0..23 (one funnel shift), keep the top
+          // three bits of each byte (0x00E0E0E0) and gather them with one multiply: x * (2^22 + 2^11 + 1) puts the
+          // r / g / b fields at bits 27..29 / 24..26 / 21..23 (all other partial products fall outside 21..29).
+          const uint32_t lo = w[b0 >> 2], hi = (b0 >> 2) + 1 < 12 ? w[(b0 >> 2) + 1] : 0u;
+          const uint32_t win = (b0 & 3) ? __funnelshift_r(lo, hi, 8 * (b0 & 3)) : lo;
+          add_bin(int(((win & 0x00E0E0E0u) * 0x00400801u) >> 21));
+        }
       }
     }
   } else {
