@@ -1,4 +1,4 @@
-"""world_size-2 gloo test of the row-sharded search: shard ranges, index offsets, the single
+"""world_size-2 / -3 gloo test of the row-sharded search: shard ranges, index offsets, the single
 all-gather and the merge order.  The local search and the merge are the oracle here (this is a
 CPU test of the host logic; the CUDA operators are covered by -m gpu tests)."""
 import os
@@ -59,20 +59,20 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.timeout(120)
-def test_two_rank_sharded_search_equals_single(tmp_path):
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_search_equals_single(tmp_path, world):
+    """2 ranks, and 3 ranks with uneven shards (1001 rows): every rank ends with the unsharded result."""
     from oracle import search as OS
     from oracle import synth
-    world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     X = synth.gaussian(1001, 32, 7)
     X[900] = X[3]
     Q = np.concatenate([X[3:4], synth.gaussian(4, 32, 8)])
-    r0 = np.load(tmp_path / "rank0.npz")
-    r1 = np.load(tmp_path / "rank1.npz")
+    ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
     for metric in ("l1", "cosine_similarity"):
         v, i = OS.topk_search(Q, X, metric, 9, dtype=np.float32)
-        for r in (r0, r1):
+        for r in ranks:
             assert np.array_equal(r[f"{metric}_i"], i), metric
             assert np.array_equal(r[f"{metric}_s"], v.astype(np.float32)), metric
-    assert list(r0["l1_i"][0, :2]) == [3, 900]
+    assert list(ranks[0]["l1_i"][0, :2]) == [3, 900]
