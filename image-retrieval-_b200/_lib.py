@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(HERE, "libb200ir.so")
 # metric ids / dtypes / flags: keep in sync with include/b200ir.h
 L1, L2, LINF, COS_SIM, COS_DIST, ANGLE, MAG_DIFF, OPTIMIZED = range(8)
 F32, BF16 = 0, 1
-FLAG_RAW, FLAG_ABS_SCORE, FLAG_NO_TENSOR, FLAG_NO_RERANK = 1, 2, 4, 8
+FLAG_RAW, FLAG_ABS_SCORE, FLAG_NO_TENSOR, FLAG_NO_RERANK, FLAG_HAVE_INDEX = 1, 2, 4, 8, 16
 RGB, HSV = 0, 1
 MAX_K = 256
 
@@ -25,6 +25,13 @@ _SIGNATURES = {
     "b200ir_topk": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp, c_i64, c_vp, c_i64, ctypes.c_int, ctypes.c_int,
                                    c_i64, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_vp, c_vp, c_vp,
                                    ctypes.c_size_t, c_vp]),
+    "b200ir_topk_fallback_counter_offset": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, c_i64, c_i64, ctypes.c_int,
+                                                              ctypes.c_int, ctypes.c_int]),
+    "b200ir_index_bytes": (ctypes.c_size_t, [ctypes.c_int, c_i64, ctypes.c_int]),
+    "b200ir_index_build": (ctypes.c_int, [ctypes.c_int, c_vp, c_i64, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),
+    "b200ir_topk_indexed": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp, c_i64, c_vp, c_i64, ctypes.c_int, ctypes.c_int,
+                                           c_i64, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_vp, c_vp, c_vp, ctypes.c_size_t,
+                                           c_vp, ctypes.c_size_t, c_vp]),
     "b200ir_pairwise_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, c_i64, c_i64, ctypes.c_int]),
     "b200ir_pairwise": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp, c_i64, c_vp, c_i64, ctypes.c_int,
                                        ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_vp, c_vp, ctypes.c_size_t, c_vp]),

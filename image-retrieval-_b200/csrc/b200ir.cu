@@ -158,13 +158,61 @@ int b200ir_row_sqnorms(const void* X, int dtype, int64_t N, int D, float* out, v
 
 size_t b200ir_topk_workspace_bytes(int metric, int dtype, int64_t nq, int64_t N, int D, int k, int flags) {
   if (!valid_metric(metric) || !valid_dtype(dtype) || nq <= 0 || N <= 0 || D <= 0 || k < 1 || k > B200IR_MAX_K) return 0;
-  if (use_tensor_path(metric, dtype, nq, N, D, k, flags)) return gemm_workspace_bytes(metric, nq, N, D, k, flags);
+  if (use_tensor_path(metric, dtype, nq, N, D, k, flags))
+    return gemm_workspace_bytes(metric, dtype, nq, N, D, k, flags, (flags & B200IR_FLAG_HAVE_INDEX) != 0);
   return make_scan_plan(metric, dtype, nq, N, D, k, false).total_bytes;
 }
+
+size_t b200ir_topk_fallback_counter_offset(int metric, int dtype, int64_t nq, int64_t N, int D, int k, int flags) {
+  if (!valid_metric(metric) || !valid_dtype(dtype) || nq <= 0 || N <= 0 || D <= 0 || k < 1 || k > B200IR_MAX_K) return ~size_t(0);
+  if (!use_tensor_path(metric, dtype, nq, N, D, k, flags) || (flags & B200IR_FLAG_NO_RERANK)) return ~size_t(0);
+  return gemm_fallback_counter_offset(dtype, nq, N, D, k, flags, (flags & B200IR_FLAG_HAVE_INDEX) != 0);
+}
+
+size_t b200ir_index_bytes(int dtype, int64_t N, int D) {
+  if (!valid_dtype(dtype) || N <= 0 || D <= 0) return 0;
+  return gemm_index_bytes(dtype, N, D);
+}
+
+int b200ir_index_build(int dtype, const void* X, int64_t N, int D, void* index, size_t index_bytes, void* stream) {
+  if (!valid_dtype(dtype) || N <= 0 || D <= 0 || !X || !index) return B200IR_E_ARG;
+  const size_t need = gemm_index_bytes(dtype, N, D);
+  if (need == 0) return B200IR_E_SHAPE;
+  if (index_bytes < need) return B200IR_E_WORKSPACE;
+  return gemm_index_build(dtype, X, N, D, static_cast<unsigned char*>(index), static_cast<cudaStream_t>(stream));
+}
+
+static int topk_impl(int metric, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D,
+                     int k, int64_t index_offset, int flags, const float* weights_host,
+                     float* out_score, int64_t* out_idx, const void* index, size_t index_bytes,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 int b200ir_topk(int metric, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D,
                 int k, int64_t index_offset, int flags, const float* weights_host,
                 float* out_score, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
+  return topk_impl(metric, dtype, Q, nq, X, N, D, k, index_offset, flags & ~B200IR_FLAG_HAVE_INDEX, weights_host, out_score, out_idx,
+                   nullptr, 0, workspace, workspace_bytes, stream);
+}
+
+int b200ir_topk_indexed(int metric, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D,
+                        int k, int64_t index_offset, int flags, const float* weights_host,
+                        float* out_score, int64_t* out_idx, const void* index, size_t index_bytes,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (!index || reinterpret_cast<uintptr_t>(index) % 256) return B200IR_E_ARG;
+  if (!valid_dtype(dtype) || N <= 0 || D <= 0) return B200IR_E_ARG;
+  const size_t need = gemm_index_bytes(dtype, N, D);
+  if (need == 0 || index_bytes < need) return B200IR_E_WORKSPACE;
+  return topk_impl(metric, dtype, Q, nq, X, N, D, k, index_offset, flags | B200IR_FLAG_HAVE_INDEX, weights_host, out_score, out_idx,
+                   index, index_bytes, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+static int topk_impl(int metric, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D,
+                     int k, int64_t index_offset, int flags, const float* weights_host,
+                     float* out_score, int64_t* out_idx, const void* index, size_t index_bytes,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  (void)index_bytes;
   if (!valid_metric(metric) || !valid_dtype(dtype) || nq < 0 || N < 0 || D <= 0) return B200IR_E_ARG;
   if (k < 1 || k > B200IR_MAX_K) return B200IR_E_K;
   if (N >= (int64_t(1) << 32)) return B200IR_E_SHAPE;      // shard-local ids are 32-bit inside the keys
@@ -185,7 +233,8 @@ int b200ir_topk(int metric, int dtype, const void* Q, int64_t nq, const void* X,
   unsigned char* ws = static_cast<unsigned char*>(workspace);
 
   if (use_tensor_path(metric, dtype, nq, N, D, k, flags)) {
-    return run_gemm_topk(metric, Q, nq, X, N, D, k, index_offset, flags, mp, out_score, out_idx, ws, st);
+    return run_gemm_topk(metric, dtype, Q, nq, X, N, D, k, index_offset, flags, mp, out_score, out_idx, ws,
+                         static_cast<const unsigned char*>(index), st);
   }
   const ScanPlan pl = make_scan_plan(metric, dtype, nq, N, D, k, false);
   cudaError_t e = run_scan(pl, dtype, Q, nq, X, N, D, k, mp, ws, nullptr, st);
@@ -194,6 +243,8 @@ int b200ir_topk(int metric, int dtype, const void* Q, int64_t nq, const void* X,
                       index_offset, out_score, out_idx, st);
   return int(e);
 }
+
+extern "C" {
 
 size_t b200ir_pairwise_workspace_bytes(int metric, int dtype, int64_t nq, int64_t N, int D) {
   if (!valid_metric(metric) || !valid_dtype(dtype) || nq <= 0 || N <= 0 || D <= 0) return 0;

@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "gemm_topk.h"
+#include "scan_plan.h"
 #include "profile.h"
 #include "select.cuh"
 
@@ -367,9 +368,17 @@ __device__ __forceinline__ float score_of(float dot, float s) {
 }
 
 // ------------------------------------------------------------------------------------ main kernel
-template <int MODE, int NCTA>
+// NT = 1: bf16 store, one MMA pass per k-block (A = the query tile, resident; B = database rows, streamed).
+// NT = 3: fp32 store as an error-compensated bf16 split x = hi + lo (hi = bf16(x), lo = bf16(x - hi), 16 mantissa
+//         bits together): q.x ~= q_hi.x_hi + q_hi.x_lo + q_lo.x_hi, all three accumulated into the same TMEM
+//         accumulator.  q_hi is the resident A operand; x_hi, x_lo and this CTA's q_lo k-block take one ring slot
+//         each (the same 16 KB), so a k-block costs three slots and twelve MMAs and the bytes staged per MMA are the
+//         same as in the bf16 kernel.  tmA2 / tmB2 are the tensor maps of the lo planes (NT = 1: unused copies).
+template <int MODE, int NCTA, int NT>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2, const Args a) {
+  static_assert(NT == 1 || (NT == 3 && NCTA == 2), "the split mode is built for the CTA-pair kernel only");
   // NCTA == 2: the CTA pair of a cluster works on two query tiles and shares every database tile: each CTA stages
   // HALF of the tile's rows (16 KB per k-block instead of 32 KB, so the ring is 6 deep), the leader issues
   // tcgen05.mma.cta_group::2 (M = 256 across the pair) and each SM's tensor core reads both halves: shared-memory
@@ -405,6 +414,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (NT == 3) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
@@ -449,17 +459,30 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int tile0 = p * a.tiles_per_part;
         const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
         for (int t = tile0; t < tile1; ++t, ++titer) {
-          for (int kb = 0; kb < a.num_kb; ++kb, ++kiter) {
-            const int s = kiter % NST;
-            const uint32_t ph = (kiter / NST) & 1;
-            t0 = DBG_T0();
-            mbar_wait(B_EMPTY(s), ph ^ 1);
-            DBG_ADD(0, t0);
-            if (rank == 0) mbar_expect_tx(B_FULL(s), B_STAGE_BYTES);                  // both halves land on the leader's barrier
-            if constexpr (NCTA == 2) tma_load_2d_2cta(smem_u32(sB + s * STAGE_BYTES), &tmB, B_FULL(s), kb * BK, t * BN + int(rank) * BN_CTA);
-            else tma_load_2d(smem_u32(sB + s * STAGE_BYTES), &tmB, B_FULL(s), kb * BK, t * BN);
-            // pull the same k-block of the tile two ahead into L2 (the shared-memory ring is only 3 k-blocks deep)
-            if ((a.opt & 1) && t + 2 < tile1) tma_prefetch_l2_2d(&tmB, kb * BK, (t + 2) * BN);
+          for (int kb = 0; kb < a.num_kb; ++kb) {
+#pragma unroll
+            for (int part = 0; part < NT; ++part, ++kiter) {          // NT = 3: x_hi, x_lo, q_lo
+              const int s = kiter % NST;
+              const uint32_t ph = (kiter / NST) & 1;
+              t0 = DBG_T0();
+              mbar_wait(B_EMPTY(s), ph ^ 1);
+              DBG_ADD(0, t0);
+              if (rank == 0) mbar_expect_tx(B_FULL(s), B_STAGE_BYTES);                  // both halves land on the leader's barrier
+              const uint32_t dst = smem_u32(sB + s * STAGE_BYTES);
+              if constexpr (NT == 3) {
+                if (part == 2) tma_load_2d_2cta(dst, &tmA2, B_FULL(s), kb * BK, qt * BM);
+                else tma_load_2d_2cta(dst, part == 0 ? &tmB : &tmB2, B_FULL(s), kb * BK, t * BN + int(rank) * BN_CTA);
+              } else if constexpr (NCTA == 2) {
+                tma_load_2d_2cta(dst, &tmB, B_FULL(s), kb * BK, t * BN + int(rank) * BN_CTA);
+              } else {
+                tma_load_2d(dst, &tmB, B_FULL(s), kb * BK, t * BN);
+              }
+            }
+            // pull the same k-block of the tile two ahead into L2 (the shared-memory ring is only a few k-blocks deep)
+            if ((a.opt & 1) && t + 2 < tile1) {
+              tma_prefetch_l2_2d(&tmB, kb * BK, (t + 2) * BN);
+              if constexpr (NT == 3) tma_prefetch_l2_2d(&tmB2, kb * BK, (t + 2) * BN);
+            }
           }
           // per-column scale of this tile: its buffer is free once the epilogue released accumulator `buf`
           // two tiles ago (already true by now in steady state: the MMAs of this tile are running)
@@ -496,27 +519,61 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           DBG_ADD(4, t0);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + uint32_t(buf * BN);
-          for (int kb = 0; kb < a.num_kb; ++kb, ++kiter) {
-            const int s = kiter % NST;
-            const uint32_t ph = (kiter / NST) & 1;
-            t0 = DBG_T0();
-            mbar_wait(B_FULL(s), ph);
-            DBG_ADD(3, t0);
-            tc_fence_after();
+          for (int kb = 0; kb < a.num_kb; ++kb) {
             const uint32_t a_addr = smem_u32(sA + kb * A_KB_BYTES);
-            const uint32_t b_addr = smem_u32(sB + s * STAGE_BYTES);
-            t0 = DBG_T0();
+            if constexpr (NT == 3) {
+              // slots: s0 = x_hi, s1 = x_lo, s2 = q_lo of this k-block
+              const int s0 = kiter % NST, s1 = (kiter + 1) % NST, s2 = (kiter + 2) % NST;
+              const uint32_t ph0 = (kiter / NST) & 1, ph1 = ((kiter + 1) / NST) & 1, ph2 = ((kiter + 2) / NST) & 1;
+              kiter += 3;
+              const uint32_t xhi = smem_u32(sB + s0 * STAGE_BYTES), xlo = smem_u32(sB + s1 * STAGE_BYTES), qlo = smem_u32(sB + s2 * STAGE_BYTES);
+              t0 = DBG_T0();
+              mbar_wait(B_FULL(s0), ph0);
+              DBG_ADD(3, t0);
+              tc_fence_after();
 #pragma unroll
-            for (int k4 = 0; k4 < BK / UMMA_K; ++k4) {
-              if constexpr (NCTA == 2)
-                tc_mma_bf16_2cta(tmem_d, make_smem_desc(a_addr + k4 * UMMA_K * 2), make_smem_desc(b_addr + k4 * UMMA_K * 2),
-                                 kInstrDesc2, (kb | k4) != 0 ? 1u : 0u);
-              else
-                tc_mma_bf16(tmem_d, make_smem_desc(a_addr + k4 * UMMA_K * 2), make_smem_desc(b_addr + k4 * UMMA_K * 2),
-                            kInstrDesc, (kb | k4) != 0 ? 1u : 0u);
+              for (int k4 = 0; k4 < BK / UMMA_K; ++k4)
+                tc_mma_bf16_2cta(tmem_d, make_smem_desc(a_addr + k4 * UMMA_K * 2), make_smem_desc(xhi + k4 * UMMA_K * 2), kInstrDesc2,
+                                 (kb | k4) != 0 ? 1u : 0u);
+              t0 = DBG_T0();
+              mbar_wait(B_FULL(s1), ph1);
+              DBG_ADD(3, t0);
+              tc_fence_after();
+#pragma unroll
+              for (int k4 = 0; k4 < BK / UMMA_K; ++k4)
+                tc_mma_bf16_2cta(tmem_d, make_smem_desc(a_addr + k4 * UMMA_K * 2), make_smem_desc(xlo + k4 * UMMA_K * 2), kInstrDesc2, 1u);
+              tc_commit_2cta(B_EMPTY(s1));
+              t0 = DBG_T0();
+              mbar_wait(B_FULL(s2), ph2);
+              DBG_ADD(3, t0);
+              tc_fence_after();
+#pragma unroll
+              for (int k4 = 0; k4 < BK / UMMA_K; ++k4)
+                tc_mma_bf16_2cta(tmem_d, make_smem_desc(qlo + k4 * UMMA_K * 2), make_smem_desc(xhi + k4 * UMMA_K * 2), kInstrDesc2, 1u);
+              tc_commit_2cta(B_EMPTY(s0));
+              tc_commit_2cta(B_EMPTY(s2));
+            } else {
+              const int s = kiter % NST;
+              const uint32_t ph = (kiter / NST) & 1;
+              ++kiter;
+              t0 = DBG_T0();
+              mbar_wait(B_FULL(s), ph);
+              DBG_ADD(3, t0);
+              tc_fence_after();
+              const uint32_t b_addr = smem_u32(sB + s * STAGE_BYTES);
+              t0 = DBG_T0();
+#pragma unroll
+              for (int k4 = 0; k4 < BK / UMMA_K; ++k4) {
+                if constexpr (NCTA == 2)
+                  tc_mma_bf16_2cta(tmem_d, make_smem_desc(a_addr + k4 * UMMA_K * 2), make_smem_desc(b_addr + k4 * UMMA_K * 2),
+                                   kInstrDesc2, (kb | k4) != 0 ? 1u : 0u);
+                else
+                  tc_mma_bf16(tmem_d, make_smem_desc(a_addr + k4 * UMMA_K * 2), make_smem_desc(b_addr + k4 * UMMA_K * 2),
+                              kInstrDesc, (kb | k4) != 0 ? 1u : 0u);
+              }
+              if constexpr (NCTA == 2) tc_commit_2cta(B_EMPTY(s)); else tc_commit(B_EMPTY(s));   // stage reusable once these MMAs retire
+              DBG_ADD(6, t0);
             }
-            if constexpr (NCTA == 2) tc_commit_2cta(B_EMPTY(s)); else tc_commit(B_EMPTY(s));   // stage reusable once these MMAs retire
-            DBG_ADD(6, t0);
           }
           if constexpr (NCTA == 2) tc_commit_2cta(T_FULL(buf)); else tc_commit(T_FULL(buf));    // accumulator complete -> epilogue
         }
@@ -696,32 +753,93 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------ side kernels
-// Per-row scale of the database operand: 1/|x| (0 for a zero row: cos := 0, geometric_metrics.py:16-17) or |x|^2.
-__global__ void row_scale_kernel(const __nv_bfloat16* __restrict__ X, int64_t N, int64_t N_pad, int D, int l2, float* __restrict__ out) {
-  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= N_pad) return;
-  if (row >= N) { if (lane == 0) out[row] = __int_as_float(0x7fc00000); return; }    // NaN masks rows past N
-  const __nv_bfloat16* x = X + row * D;
-  float ss = 0.f;
-  for (int d = lane * 8; d < D; d += 256) {        // D % 8 == 0 on this path
-    const uint4 w = __ldg(reinterpret_cast<const uint4*>(x + d));
-    const float f[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
-#pragma unroll
-    for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if (lane == 0) out[row] = l2 ? ss : (ss > 0.f ? 1.0f / sqrtf(ss) : 0.f);
+// 8 consecutive elements of a row as fp32 (16-byte loads: D % 8 == 0 and 16-byte aligned bases on this path)
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&f)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 w = __ldg(reinterpret_cast<const uint4*>(p));
+  f[0] = bf16_lo(w.x); f[1] = bf16_hi(w.x); f[2] = bf16_lo(w.y); f[3] = bf16_hi(w.y);
+  f[4] = bf16_lo(w.z); f[5] = bf16_hi(w.z); f[6] = bf16_lo(w.w); f[7] = bf16_hi(w.w);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+  return uint32_t(__bfloat16_as_ushort(lo)) | (uint32_t(__bfloat16_as_ushort(hi)) << 16);
 }
 
-// One warp per query: merge the P partition lists, optionally re-rank the kp candidates with exact fp32
-// arithmetic (direct dot / direct sum of squared differences, fp32, no cancellation), write the k winners.
-template <int E>
+// Per-row state of the B operand, computed ONCE per store (b200ir_index_build) or per call when no index is given:
+//   rnorm[i] = 1/|x_i| (0 for a zero row: cos := 0, geometric_metrics.py:16-17), sqnorm[i] = |x_i|^2, NaN past row N
+//   (NaN scores vanish in the epilogue's max reduction), *maxsq = max_i |x_i|^2 (ordered bits; bounds the L2
+//   certificate), and for fp32 rows the bf16 planes hi = bf16(x), lo = bf16(x - hi) of the split described at the kernel.
+// One warp per row.
+template <typename T>
+__global__ void __launch_bounds__(256)
+index_rows_kernel(const T* __restrict__ X, int64_t N, int64_t N_pad, int D, float* __restrict__ rnorm, float* __restrict__ sqnorm,
+                  unsigned int* __restrict__ maxsq, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  __shared__ float blockmax[8];
+  float ss = 0.f;
+  if (row < N) {
+    const T* x = X + row * D;
+    for (int d = lane * 8; d < D; d += 256) {
+      float f[8];
+      load8<T>(x + d, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+      if (hi != nullptr) {
+        __nv_bfloat16 h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          h[e] = __float2bfloat16_rn(f[e]);
+          l[e] = __float2bfloat16_rn(f[e] - __bfloat162float(h[e]));
+        }
+        *reinterpret_cast<uint4*>(hi + row * D + d) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+        *reinterpret_cast<uint4*>(lo + row * D + d) = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (rnorm != nullptr && row < N_pad && lane == 0) {
+    const float nan = __int_as_float(0x7fc00000);
+    rnorm[row] = row < N ? (ss > 0.f ? 1.0f / sqrtf(ss) : 0.f) : nan;
+    sqnorm[row] = row < N ? ss : nan;
+  }
+  if (maxsq != nullptr) {
+    if (lane == 0) blockmax[threadIdx.x >> 5] = (row < N && ss == ss) ? ss : 0.f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = 0.f;
+      for (int w = 0; w < 8; ++w) m = fmaxf(m, blockmax[w]);
+      if (m > 0.f) atomicMax(maxsq, __float_as_uint(m));            // non-negative floats order like their bit patterns
+    }
+  }
+}
+
+// A-posteriori exactness certificate (see gemm_finalize_kernel) and the list of queries that failed it
+struct Certify {
+  float u_eff;                 // |computed dot - exact dot| <= u_eff * |q| * |x| on the tensor-core pass
+  const unsigned int* maxsq;   // max_i |x_i|^2 of the store
+  int* fb_count;               // number of uncertified queries (zeroed per call), or nullptr: no certificate
+  int* fb_list;                // [nq] their ids
+};
+
+// One warp per query: merge the P partition lists, re-rank the kp candidates with exact fp32 arithmetic on the
+// original rows (direct dot / direct sum of squared differences: no split, no cancellation), write the k winners.
+//
+// Certificate.  Every row that is NOT among the kp candidates was dropped against kp rows whose tensor-core score was
+// at least as good, so its tensor-core rank value is >= a_last, the rank value of the worst candidate kept.  With
+// |dot~ - dot| <= u_eff |q||x| its exact score is bounded; if the k-th best EXACT score among the candidates is
+// strictly better than that bound, no dropped row can enter or tie the top-k and the result equals the exact scan's.
+// Otherwise (near-ties denser than the kp - k margin, duplicates, huge-norm outliers) the query is appended to
+// fb_list and re-done by the exact CUDA-core scan.
+template <int E, typename T>
 __global__ void __launch_bounds__(128)
-gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __restrict__ thr_g, const __nv_bfloat16* __restrict__ Q,
-                     const __nv_bfloat16* __restrict__ X, int nq, int D, int P, int kp, int k, int mode, int rerank, MetricParams mp,
-                     int64_t index_offset,
+gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __restrict__ thr_g, const T* __restrict__ Q,
+                     const T* __restrict__ X, int nq, int D, int P, int kp, int k, int mode, int rerank, MetricParams mp,
+                     int64_t index_offset, Certify cert,
                      float* __restrict__ out_score, int64_t* __restrict__ out_idx) {
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -761,18 +879,28 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
       __syncwarp();
     }
   }
+  // tensor-core rank value of the worst candidate kept (only meaningful when the list is full: otherwise nothing was
+  // ever dropped for this query and every row of the store is a candidate)
+  float a_last = 0.f;
+  {
+    uint64_t kl = kKeyInf;
+#pragma unroll
+    for (int e = 0; e < E; ++e) if (e == (kp - 1) % E) kl = r[e];
+    kl = shfl_u64(kl, (kp - 1) / E);
+    a_last = key_rank(kl);
+  }
+  const bool list_full = kept >= kp;
 
   // query row in registers: lane holds elements [8*(lane + 32 j), +8), j = 0, 1 (D <= 512)
-  const __nv_bfloat16* qrow = Q + int64_t(q) * D;
+  const T* qrow = Q + int64_t(q) * D;
   float qf[2][8];
   float qss = 0.f;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const int d = (lane + 32 * j) * 8;
-    uint4 w = make_uint4(0, 0, 0, 0);
-    if (d < D) w = __ldg(reinterpret_cast<const uint4*>(qrow + d));
-    qf[j][0] = bf16_lo(w.x); qf[j][1] = bf16_hi(w.x); qf[j][2] = bf16_lo(w.y); qf[j][3] = bf16_hi(w.y);
-    qf[j][4] = bf16_lo(w.z); qf[j][5] = bf16_hi(w.z); qf[j][6] = bf16_lo(w.w); qf[j][7] = bf16_hi(w.w);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qf[j][e] = 0.f;
+    if (d < D) load8<T>(qrow + d, qf[j]);
 #pragma unroll
     for (int e = 0; e < 8; ++e) qss = fmaf(qf[j][e], qf[j][e], qss);
   }
@@ -790,14 +918,14 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
       const uint32_t idx = key_index(key);
       float rank;
       if (rerank) {
-        const __nv_bfloat16* xrow = X + int64_t(idx) * D;
+        const T* xrow = X + int64_t(idx) * D;
         float dot = 0.f, xss = 0.f, d2 = 0.f;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int d = (lane + 32 * j) * 8;
           if (d < D) {
-            const uint4 w = __ldg(reinterpret_cast<const uint4*>(xrow + d));
-            const float xf[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+            float xf[8];
+            load8<T>(xrow + d, xf);
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
               dot = fmaf(xf[t], qf[j][t], dot);
@@ -831,6 +959,25 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
 #pragma unroll
   for (int e = 0; e < E; ++e) if (lane * E + e >= kp) r[e] = kKeyInf;
   warp_sort<E>(r, lane);
+  if (rerank && cert.fb_count != nullptr && list_full) {
+    uint64_t kk = kKeyInf;
+#pragma unroll
+    for (int e = 0; e < E; ++e) if (e == (k - 1) % E) kk = r[e];
+    kk = shfl_u64(kk, (k - 1) / E);
+    const float exact_k = key_rank(kk);                          // k-th best exact rank value (smaller = better)
+    bool ok;
+    if (mode == MODE_L2) {
+      // dropped row: d^2 = |q|^2 + (|x|^2 - 2 q.x) >= |q|^2 + a_last - eps
+      const float xmax2 = __uint_as_float(*cert.maxsq);
+      const float eps = 2.0f * cert.u_eff * qn * sqrtf(xmax2) + 9.6e-7f * (xmax2 + qss);
+      ok = exact_k < (qss + a_last) - eps;
+    } else {
+      // dropped row: cos <= (-a_last) / |q| + u_eff   (a_last = -dot~/|x|, or -|dot~|/|x|)
+      const float bound = qn != 0.f ? (-a_last) / qn + cert.u_eff : INFINITY;
+      ok = -exact_k > bound;
+    }
+    if (!ok && lane == 0) cert.fb_list[atomicAdd(cert.fb_count, 1)] = q;
+  }
   emit_topk<E>(r, lane, k, mp, index_offset, out_score, out_idx, int64_t(q));
 }
 
@@ -863,9 +1010,32 @@ static bool encode_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, i
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Prepared per-store state (b200ir_index_build, or built per call inside the workspace when no index is passed)
+struct IndexLayout {
+  int64_t N_pad;
+  size_t off_rnorm, off_sqnorm, off_max, off_hi, off_lo, total_bytes;
+};
+
+static IndexLayout index_layout(int dtype, int64_t N, int D) {
+  IndexLayout L{};
+  L.N_pad = ceil_div64(N, BN) * BN;
+  size_t off = 0;
+  L.off_rnorm = off; off += round_up64(size_t(L.N_pad) * 4, 256);
+  L.off_sqnorm = off; off += round_up64(size_t(L.N_pad) * 4, 256);
+  L.off_max = off; off += 256;
+  L.off_hi = off;
+  L.off_lo = off;
+  if (dtype == B200IR_F32) {
+    off += round_up64(size_t(N) * D * 2, 256);
+    L.off_lo = off; off += round_up64(size_t(N) * D * 2, 256);
+  }
+  L.total_bytes = off;
+  return L;
+}
+
 struct Plan {
   int num_qtiles, num_qgroups, ncta, total_tiles, P, tiles_per_part, kp, cap, grid, num_kb;
-  size_t off_scale, off_thr, off_lvl, off_cand, off_partial, total_bytes;
+  size_t off_thr, off_lvl, off_cand, off_partial, off_fb, off_qhi, off_qlo, off_index, off_fbws, total_bytes;
 };
 
 static int num_sms() {
@@ -878,15 +1048,15 @@ static int num_sms() {
   return n;
 }
 
-// cluster size of the main kernel: 2 (tcgen05 cta_group::2) unless B200IR_GEMM_NCTA=1
-static int gemm_ncta() {
+// cluster size of the main kernel: 2 (tcgen05 cta_group::2) unless B200IR_GEMM_NCTA=1 (bf16 stores only)
+static int gemm_ncta(int dtype) {
   static const int n = (getenv("B200IR_GEMM_NCTA") && atoi(getenv("B200IR_GEMM_NCTA")) == 1) ? 1 : 2;
-  return n;
+  return dtype == B200IR_F32 ? 2 : n;
 }
 
-static Plan make_plan(int64_t nq, int64_t N, int D, int k, int flags, int sms) {
+static Plan make_plan(int dtype, int64_t nq, int64_t N, int D, int k, int flags, int sms, bool internal_index, size_t fallback_bytes) {
   Plan pl{};
-  pl.ncta = gemm_ncta();
+  pl.ncta = gemm_ncta(dtype);
   pl.num_kb = (D + BK - 1) / BK;
   pl.num_qtiles = int(ceil_div64(nq, BM));
   pl.num_qgroups = (pl.num_qtiles + pl.ncta - 1) / pl.ncta;
@@ -916,60 +1086,122 @@ static Plan make_plan(int64_t nq, int64_t N, int D, int k, int flags, int sms) {
   const int64_t units = int64_t(pl.num_qgroups) * pl.P;
   pl.grid = int(units < nclusters_max ? units : nclusters_max) * pl.ncta;
   size_t off = 0;
-  pl.off_scale = off; off += round_up64(size_t(pl.total_tiles) * BN * 4, 256);
   pl.off_thr = off; off += round_up64(size_t(pl.num_qgroups) * pl.ncta * BM * 4, 256);
   pl.off_lvl = off; off += pl.P <= 32 ? round_up64(size_t(pl.num_qgroups) * pl.ncta * BM * kLevels * pl.P * 4, 256) : 0;
   pl.off_cand = off; off += round_up64(size_t(pl.grid) * BM * pl.cap * 8, 256);
   pl.off_partial = off; off += round_up64(size_t(nq) * pl.P * pl.kp * 8, 256);
+  pl.off_fb = off; off += round_up64(size_t(nq) * 4 + 256, 256);                        // [count | pad | list]
+  pl.off_qhi = pl.off_qlo = off;
+  if (dtype == B200IR_F32) {
+    off += round_up64(size_t(nq) * D * 2, 256);
+    pl.off_qlo = off; off += round_up64(size_t(nq) * D * 2, 256);
+  }
+  pl.off_index = off;
+  if (internal_index) off += index_layout(dtype, N, D).total_bytes;
+  pl.off_fbws = off; off += fallback_bytes;
   pl.total_bytes = off;
   return pl;
 }
 
+template <typename T>
+static cudaError_t launch_index_rows(const void* X, int64_t N, int64_t N_pad, int D, float* rnorm, float* sqnorm, unsigned int* maxsq,
+                                     __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st) {
+  index_rows_kernel<T><<<unsigned(ceil_div64(N_pad, 8)), 256, 0, st>>>(static_cast<const T*>(X), N, N_pad, D, rnorm, sqnorm, maxsq, hi, lo);
+  return cudaGetLastError();
+}
+
+static cudaError_t build_index(int dtype, const void* X, int64_t N, int D, unsigned char* index, cudaStream_t st) {
+  const IndexLayout L = index_layout(dtype, N, D);
+  cudaError_t e = cudaMemsetAsync(index + L.off_max, 0, 256, st);
+  if (e != cudaSuccess) return e;
+  float* rn = reinterpret_cast<float*>(index + L.off_rnorm);
+  float* sq = reinterpret_cast<float*>(index + L.off_sqnorm);
+  unsigned int* mx = reinterpret_cast<unsigned int*>(index + L.off_max);
+  if (dtype == B200IR_F32)
+    return launch_index_rows<float>(X, N, L.N_pad, D, rn, sq, mx, reinterpret_cast<__nv_bfloat16*>(index + L.off_hi),
+                                    reinterpret_cast<__nv_bfloat16*>(index + L.off_lo), st);
+  return launch_index_rows<__nv_bfloat16>(X, N, L.N_pad, D, rn, sq, mx, nullptr, nullptr, st);
+}
+
 }  // namespace gemm
 
+static int clamp_sms() {
+  int sms = gemm::num_sms();
+  return sms > kNumSMs ? kNumSMs : sms;
+}
+
 bool gemm_path_supported(int metric, int dtype, int64_t nq, int64_t N, int D, int k, int flags) {
-  if (dtype != B200IR_BF16) return false;
+  if (dtype != B200IR_BF16 && dtype != B200IR_F32) return false;
   if (!(metric == B200IR_L2 || metric == B200IR_COS_SIM || metric == B200IR_COS_DIST || metric == B200IR_ANGLE)) return false;
   if (D % 8 != 0 || D > gemm::MAX_KB * gemm::BK || D < 16) return false;
   if (nq < 32 || N < 4 * gemm::BN) return false;      // tiny problems stay on the scan path
   if (k > 224) return false;
-  (void)flags;
   return true;
 }
 
-size_t gemm_workspace_bytes(int metric, int64_t nq, int64_t N, int D, int k, int flags) {
-  (void)metric;
-  int sms = gemm::num_sms();
-  if (sms > kNumSMs) sms = kNumSMs;
-  return gemm::make_plan(nq, N, D, k, flags, sms).total_bytes;
+size_t gemm_fallback_counter_offset(int dtype, int64_t nq, int64_t N, int D, int k, int flags, bool have_index) {
+  return gemm::make_plan(dtype, nq, N, D, k, flags, clamp_sms(), !have_index, 0).off_fb;
 }
 
-int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t N, int D, int k, int64_t index_offset,
-                  int flags, const MetricParams& mp, float* out_score, int64_t* out_idx, unsigned char* ws, cudaStream_t st) {
+size_t gemm_index_bytes(int dtype, int64_t N, int D) {
+  if (N <= 0 || D <= 0 || D % 8 != 0 || D > gemm::MAX_KB * gemm::BK || D < 16) return 0;
+  return gemm::index_layout(dtype, N, D).total_bytes;
+}
+
+int gemm_index_build(int dtype, const void* X, int64_t N, int D, unsigned char* index, cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(index) & 255)) return B200IR_E_ALIGN;
+  ProfileScope ps(PT_PREP, st);
+  return int(gemm::build_index(dtype, X, N, D, index, st));
+}
+
+size_t gemm_workspace_bytes(int metric, int dtype, int64_t nq, int64_t N, int D, int k, int flags, bool have_index) {
+  (void)metric;
+  const size_t fb = make_fallback_plan(dtype, nq, N, D, k).total_bytes;
+  return gemm::make_plan(dtype, nq, N, D, k, flags, clamp_sms(), !have_index, fb).total_bytes;
+}
+
+int run_gemm_topk(int metric, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D, int k, int64_t index_offset,
+                  int flags, const MetricParams& mp, float* out_score, int64_t* out_idx, unsigned char* ws,
+                  const unsigned char* index, cudaStream_t st) {
   using namespace gemm;
   if ((reinterpret_cast<uintptr_t>(Q) & 15) || (reinterpret_cast<uintptr_t>(X) & 15)) return B200IR_E_ALIGN;
-  int sms = num_sms();
-  if (sms > kNumSMs) sms = kNumSMs;
-  const Plan pl = make_plan(nq, N, D, k, flags, sms);
+  const bool f32 = dtype == B200IR_F32;
+  const FallbackPlan fbp = make_fallback_plan(dtype, nq, N, D, k);
+  const Plan pl = make_plan(dtype, nq, N, D, k, flags, clamp_sms(), index == nullptr, fbp.total_bytes);
   const int mode = metric == B200IR_L2 ? MODE_L2 : ((flags & B200IR_FLAG_ABS_SCORE) ? MODE_ABSCOS : MODE_COS);
+  const IndexLayout IL = index_layout(dtype, N, D);
 
-  CUtensorMap tmA, tmB;
-  if (!encode_bf16_rows(&tmA, Q, nq, D, BM) || !encode_bf16_rows(&tmB, X, N, D, BN / pl.ncta)) return B200IR_E_DEVICE;
-
-  float* scale = reinterpret_cast<float*>(ws + pl.off_scale);
   {
     ProfileScope ps(PT_PREP, st);
-    const int64_t N_pad = int64_t(pl.total_tiles) * BN;
-    row_scale_kernel<<<unsigned(ceil_div64(N_pad, 8)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(X), N, N_pad, D, mode == MODE_L2 ? 1 : 0, scale);
-    cudaError_t em = cudaMemsetAsync(ws + pl.off_thr, 0xff, pl.off_cand - pl.off_thr, st);      // thresholds + level slots
+    if (index == nullptr) {                                        // no prepared index: build the per-store state now
+      cudaError_t e = build_index(dtype, X, N, D, ws + pl.off_index, st);
+      if (e != cudaSuccess) return int(e);
+      index = ws + pl.off_index;
+    }
+    // per-search state: thresholds + level slots (0xff = none published), fallback counter
+    cudaError_t em = cudaMemsetAsync(ws + pl.off_thr, 0xff, pl.off_cand - pl.off_thr, st);
+    if (em == cudaSuccess) em = cudaMemsetAsync(ws + pl.off_fb, 0, 256, st);
     if (em != cudaSuccess) return int(em);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return int(e);
+    if (f32) {                                                     // bf16 hi / lo planes of the query batch
+      cudaError_t e = launch_index_rows<float>(Q, nq, nq, D, nullptr, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qhi),
+                                               reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qlo), st);
+      if (e != cudaSuccess) return int(e);
+    }
   }
+
+  CUtensorMap tmA, tmA2, tmB, tmB2;
+  const void* a_hi = f32 ? static_cast<const void*>(ws + pl.off_qhi) : Q;
+  const void* a_lo = f32 ? static_cast<const void*>(ws + pl.off_qlo) : Q;
+  const void* b_hi = f32 ? static_cast<const void*>(index + IL.off_hi) : X;
+  const void* b_lo = f32 ? static_cast<const void*>(index + IL.off_lo) : X;
+  if (!encode_bf16_rows(&tmA, a_hi, nq, D, BM) || !encode_bf16_rows(&tmA2, a_lo, nq, D, BM) ||
+      !encode_bf16_rows(&tmB, b_hi, N, D, BN / pl.ncta) || !encode_bf16_rows(&tmB2, b_lo, N, D, BN / pl.ncta))
+    return B200IR_E_DEVICE;
+
   Args a{};
   a.nq = int(nq); a.N = N; a.D = D; a.num_kb = pl.num_kb; a.num_qtiles = pl.num_qtiles; a.num_qgroups = pl.num_qgroups; a.P = pl.P;
   a.tiles_per_part = pl.tiles_per_part; a.total_tiles = pl.total_tiles; a.kp = pl.kp; a.cap = pl.cap;
-  a.colscale = scale;
+  a.colscale = reinterpret_cast<const float*>(index + (mode == MODE_L2 ? IL.off_sqnorm : IL.off_rnorm));
   a.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
   a.partial = reinterpret_cast<uint64_t*>(ws + pl.off_partial);
   a.thr_g = reinterpret_cast<uint32_t*>(ws + pl.off_thr);
@@ -1003,16 +1235,20 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a);
+      return cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, tmB2, a);
     };
-    if (pl.ncta == 2) {
-      if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 2>, 2);
-      else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 2>, 2);
-      else e = launch(gemm_topk_kernel<MODE_L2, 2>, 2);
+    if (f32) {
+      if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 2, 3>, 2);
+      else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 2, 3>, 2);
+      else e = launch(gemm_topk_kernel<MODE_L2, 2, 3>, 2);
+    } else if (pl.ncta == 2) {
+      if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 2, 1>, 2);
+      else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 2, 1>, 2);
+      else e = launch(gemm_topk_kernel<MODE_L2, 2, 1>, 2);
     } else {
-      if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 1>, 1);
-      else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 1>, 1);
-      else e = launch(gemm_topk_kernel<MODE_L2, 1>, 1);
+      if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 1, 1>, 1);
+      else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 1, 1>, 1);
+      else e = launch(gemm_topk_kernel<MODE_L2, 1, 1>, 1);
     }
     if (e != cudaSuccess) return int(e);
     e = cudaGetLastError();
@@ -1033,17 +1269,40 @@ int run_gemm_topk(int metric, const void* Q, int64_t nq, const void* X, int64_t 
       fprintf(stderr, "  %-22s mean %14.0f  max %14.0f\n", names[sidx], sum / pl.grid, mx);
     }
   }
+  const int rerank = (flags & B200IR_FLAG_NO_RERANK) ? 0 : 1;
+  int* fb_count = reinterpret_cast<int*>(ws + pl.off_fb);
+  int* fb_list = reinterpret_cast<int*>(ws + pl.off_fb + 256);
   {
-    const int rerank = (flags & B200IR_FLAG_NO_RERANK) ? 0 : 1;
     ProfileScope ps(rerank ? PT_RERANK : PT_FINALIZE, st);
     const int blocks = int(ceil_div64(nq, 4));
-    const __nv_bfloat16* Qb = static_cast<const __nv_bfloat16*>(Q);
-    const __nv_bfloat16* Xb = static_cast<const __nv_bfloat16*>(X);
-    if (pl.kp <= 128)
-      gemm_finalize_kernel<8><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, out_score, out_idx);
-    else
-      gemm_finalize_kernel<16><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, out_score, out_idx);
+    // u_eff: bound on |dot~ - dot| / (|q||x|) of the tensor-core pass.  bf16 store: products are exact in fp32, only the
+    // accumulation order differs (D/16 accumulate steps).  fp32 store: the split drops q_lo.x_lo and the residuals of
+    // hi + lo (<= 3 * 2^-18 together) and accumulates 3 D / 16 steps.  Both constants carry a >= 4x margin over that
+    // analysis; tests/test_gpu_tensor_fp32.py measures the actual worst error against them.
+    Certify cert{f32 ? 6.1035156e-5f : 1.5258789e-5f, reinterpret_cast<const unsigned int*>(index + IL.off_max),
+                 rerank ? fb_count : nullptr, fb_list};
+    if (f32) {
+      const float* Qf = static_cast<const float*>(Q);
+      const float* Xf = static_cast<const float*>(X);
+      if (pl.kp <= 128)
+        gemm_finalize_kernel<8, float><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qf, Xf, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, cert, out_score, out_idx);
+      else
+        gemm_finalize_kernel<16, float><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qf, Xf, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, cert, out_score, out_idx);
+    } else {
+      const __nv_bfloat16* Qb = static_cast<const __nv_bfloat16*>(Q);
+      const __nv_bfloat16* Xb = static_cast<const __nv_bfloat16*>(X);
+      if (pl.kp <= 128)
+        gemm_finalize_kernel<8, __nv_bfloat16><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, cert, out_score, out_idx);
+      else
+        gemm_finalize_kernel<16, __nv_bfloat16><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, cert, out_score, out_idx);
+    }
     cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return int(e);
+  }
+  if (rerank) {
+    // queries whose top-k could not be certified are re-done by the exact CUDA-core scan (device-side count: the
+    // launches below are no-ops when it is zero)
+    cudaError_t e = run_fallback(fbp, dtype, Q, nq, X, N, D, k, mp, fb_count, fb_list, ws + pl.off_fbws, index_offset, out_score, out_idx, st);
     if (e != cudaSuccess) return int(e);
   }
   return 0;

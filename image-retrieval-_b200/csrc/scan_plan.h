@@ -41,6 +41,10 @@ struct ScanArgs {
   uint64_t* partial;      // [nq, P, k] sorted keys            (top-k mode)
   float* out_all;         // [nq, N] metric values, or nullptr  (pairwise mode)
   MetricParams mp;
+  // fallback mode (queries that failed the tensor path's exactness certificate): the launch serves positions
+  // [gate_base, gate_base + nq) of a device-side list whose length *gate is only known on the device
+  const int* gate;        // nullptr: plain launch
+  int gate_base;
   // all-pairs evaluation mode (K_EVAL): queries == database rows, pairs i < j only
   const int32_t* cat;     // [N] object category of each row
   const int32_t* col;     // [N] colour of each row
@@ -115,6 +119,21 @@ inline ScanPlan make_scan_plan(int metric, int dtype, int64_t nq, int64_t N, int
   cudaError_t launch_scan_##kind##_bf16(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, int TQ, size_t smem, cudaStream_t st);
 B200IR_DECL_SCAN(K_L1) B200IR_DECL_SCAN(K_L2) B200IR_DECL_SCAN(K_LINF) B200IR_DECL_SCAN(K_DOT) B200IR_DECL_SCAN(K_MULTI)
 #undef B200IR_DECL_SCAN
+
+// Exact re-do of the queries a tensor-core search could not certify (gemm_topk.cu).  Their number is only known on the
+// device, so the work is cut into tiers of 8 / 64 / 512 / rest list positions, each a scan launch shaped for its size
+// (few queries -> many row partitions) whose CTAs exit at once when the list is shorter than their tier.
+constexpr int kFallbackTiers = 4;
+struct FallbackPlan {
+  int ntiers, D_pad, nq_pad, sortn;
+  int base[kFallbackTiers], count[kFallbackTiers], G[kFallbackTiers], P[kFallbackTiers];
+  int64_t rows_per_part[kFallbackTiers];
+  size_t smem, off_qf, off_qn, off_partial[kFallbackTiers], total_bytes;
+};
+FallbackPlan make_fallback_plan(int dtype, int64_t nq, int64_t N, int D, int k);
+cudaError_t run_fallback(const FallbackPlan& fp, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D, int k,
+                         const MetricParams& mp, const int* fb_count, const int* fb_list, unsigned char* ws, int64_t index_offset,
+                         float* out_score, int64_t* out_idx, cudaStream_t st);
 
 cudaError_t launch_prep_queries(int dtype, const void* Q, int nq, int D, int nq_pad, int D_pad, float* Qf, float* qn,
                                 cudaStream_t st);

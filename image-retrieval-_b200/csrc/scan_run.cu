@@ -1,5 +1,6 @@
 // Scan driver: query preparation + dispatch to the per-(kind, dtype) kernel families.
 #include "scan_topk.cuh"
+#include "select.cuh"
 #include "profile.h"
 
 #include <cstring>
@@ -34,6 +35,19 @@ static void setup_tma(ScanArgs& a, int dtype, int TQ, int nq_pad, size_t smem, C
   a.use_tma = 1;
 }
 
+static cudaError_t dispatch_scan(int kind, bool f32, const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, int TQ, size_t smem,
+                                 cudaStream_t st) {
+  ProfileScope ps(PT_SCAN, st);
+  switch (kind) {
+    case K_L1:    return f32 ? launch_scan_K_L1_f32(tmX, tmQ, a, TQ, smem, st)    : launch_scan_K_L1_bf16(tmX, tmQ, a, TQ, smem, st);
+    case K_L2:    return f32 ? launch_scan_K_L2_f32(tmX, tmQ, a, TQ, smem, st)    : launch_scan_K_L2_bf16(tmX, tmQ, a, TQ, smem, st);
+    case K_LINF:  return f32 ? launch_scan_K_LINF_f32(tmX, tmQ, a, TQ, smem, st)  : launch_scan_K_LINF_bf16(tmX, tmQ, a, TQ, smem, st);
+    case K_DOT:   return f32 ? launch_scan_K_DOT_f32(tmX, tmQ, a, TQ, smem, st)   : launch_scan_K_DOT_bf16(tmX, tmQ, a, TQ, smem, st);
+    case K_MULTI: return f32 ? launch_scan_K_MULTI_f32(tmX, tmQ, a, TQ, smem, st) : launch_scan_K_MULTI_bf16(tmX, tmQ, a, TQ, smem, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 cudaError_t run_scan(const ScanPlan& pl, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D, int k,
                      const MetricParams& mp, unsigned char* ws, float* out_all, cudaStream_t st) {
   float* Qf = reinterpret_cast<float*>(ws + pl.off_qf);
@@ -49,18 +63,82 @@ cudaError_t run_scan(const ScanPlan& pl, int dtype, const void* Q, int64_t nq, c
   a.partial = reinterpret_cast<uint64_t*>(ws + pl.off_partial);
   a.out_all = out_all;
   a.mp = mp;
-  const bool f32 = dtype == B200IR_F32;
   CUtensorMap tmX, tmQ;
   setup_tma(a, dtype, pl.TQ, pl.nq_pad, pl.smem, &tmX, &tmQ);
-  ProfileScope ps(PT_SCAN, st);
-  switch (scan_kind_of(mp.metric)) {
-    case K_L1:    return f32 ? launch_scan_K_L1_f32(tmX, tmQ, a, pl.TQ, pl.smem, st)    : launch_scan_K_L1_bf16(tmX, tmQ, a, pl.TQ, pl.smem, st);
-    case K_L2:    return f32 ? launch_scan_K_L2_f32(tmX, tmQ, a, pl.TQ, pl.smem, st)    : launch_scan_K_L2_bf16(tmX, tmQ, a, pl.TQ, pl.smem, st);
-    case K_LINF:  return f32 ? launch_scan_K_LINF_f32(tmX, tmQ, a, pl.TQ, pl.smem, st)  : launch_scan_K_LINF_bf16(tmX, tmQ, a, pl.TQ, pl.smem, st);
-    case K_DOT:   return f32 ? launch_scan_K_DOT_f32(tmX, tmQ, a, pl.TQ, pl.smem, st)   : launch_scan_K_DOT_bf16(tmX, tmQ, a, pl.TQ, pl.smem, st);
-    case K_MULTI: return f32 ? launch_scan_K_MULTI_f32(tmX, tmQ, a, pl.TQ, pl.smem, st) : launch_scan_K_MULTI_bf16(tmX, tmQ, a, pl.TQ, pl.smem, st);
-    default: return cudaErrorInvalidValue;
+  return dispatch_scan(scan_kind_of(mp.metric), dtype == B200IR_F32, tmX, tmQ, a, pl.TQ, pl.smem, st);
+}
+
+FallbackPlan make_fallback_plan(int dtype, int64_t nq, int64_t N, int D, int k) {
+  FallbackPlan fp{};
+  const int esz = dtype == B200IR_F32 ? 4 : 2;
+  const int DKE = kRowChunkBytes / esz;
+  const int TQ = 8;
+  fp.D_pad = int(round_up64(D, DKE));
+  fp.nq_pad = int(round_up64(nq, TQ));
+  fp.sortn = scan_sortn(k);
+  fp.smem = size_t(kScanStages) * scan_stage_bytes(TQ, DKE) + size_t(TQ) * fp.sortn * 8 + TQ * 16 + 64;
+  int ctas_per_sm = int((227 * 1024) / (fp.smem + 1024));
+  ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+  const int64_t target = int64_t(kNumSMs) * ctas_per_sm;
+  const int64_t ntiles = ceil_div64(N, kScanThreads);
+  size_t off = 0;
+  fp.off_qf = off; off += round_up64(size_t(fp.nq_pad) * fp.D_pad * 4, 256);
+  fp.off_qn = off; off += round_up64(size_t(fp.nq_pad) * 4, 256);
+  const int sizes[kFallbackTiers] = {8, 64, 512, 1 << 30};
+  int base = 0;
+  for (int t = 0; t < kFallbackTiers && base < fp.nq_pad; ++t) {
+    const int cnt = int(fp.nq_pad - base < sizes[t] ? fp.nq_pad - base : sizes[t]);
+    fp.base[t] = base; fp.count[t] = cnt; fp.G[t] = cnt / TQ;
+    int64_t P = target / fp.G[t];
+    P = P < 1 ? 1 : (P > ntiles ? ntiles : P);
+    P = P < 1 ? 1 : P;
+    fp.rows_per_part[t] = round_up64(ceil_div64(N, P), kScanThreads);
+    fp.P[t] = int(ceil_div64(N, fp.rows_per_part[t]));
+    if (fp.P[t] < 1) fp.P[t] = 1;
+    fp.off_partial[t] = off; off += round_up64(size_t(cnt) * fp.P[t] * k * 8, 256);
+    base += cnt;
+    fp.ntiers = t + 1;
   }
+  fp.total_bytes = off;
+  return fp;
+}
+
+cudaError_t run_fallback(const FallbackPlan& fp, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D, int k,
+                         const MetricParams& mp, const int* fb_count, const int* fb_list, unsigned char* ws, int64_t index_offset,
+                         float* out_score, int64_t* out_idx, cudaStream_t st) {
+  (void)nq;
+  float* Qf = reinterpret_cast<float*>(ws + fp.off_qf);
+  float* qn = reinterpret_cast<float*>(ws + fp.off_qn);
+  {
+    ProfileScope ps(PT_PREP, st);
+    const int blocks = int(ceil_div64(fp.nq_pad, 8));
+    if (dtype == B200IR_F32)
+      prep_queries_gather_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(Q), fb_list, fb_count, D, fp.nq_pad, fp.D_pad, Qf, qn);
+    else
+      prep_queries_gather_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(Q), fb_list, fb_count, D, fp.nq_pad, fp.D_pad, Qf, qn);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  const int esz = dtype == B200IR_F32 ? 4 : 2;
+  for (int t = 0; t < fp.ntiers; ++t) {
+    ScanArgs a{};
+    a.X = X; a.N = N; a.D = D; a.D_pad = fp.D_pad;
+    a.Qf = Qf + size_t(fp.base[t]) * fp.D_pad; a.qnorm = qn + fp.base[t]; a.nq = fp.count[t];
+    a.G = fp.G[t]; a.P = fp.P[t]; a.rows_per_part = fp.rows_per_part[t]; a.k = k; a.sortn = fp.sortn;
+    a.aligned = ((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (int64_t(D) * esz) % 16 == 0) ? 1 : 0;
+    a.partial = reinterpret_cast<uint64_t*>(ws + fp.off_partial[t]);
+    a.out_all = nullptr;
+    a.mp = mp;
+    a.gate = fb_count; a.gate_base = fp.base[t];
+    CUtensorMap tmX, tmQ;
+    setup_tma(a, dtype, 8, fp.count[t], fp.smem, &tmX, &tmQ);
+    cudaError_t e = dispatch_scan(scan_kind_of(mp.metric), dtype == B200IR_F32, tmX, tmQ, a, 8, fp.smem, st);
+    if (e != cudaSuccess) return e;
+    e = launch_finalize(a.partial, fp.count[t], int64_t(fp.P[t]) * k, k, mp, index_offset, out_score, out_idx, st,
+                        fb_list + fp.base[t], fb_count, fp.base[t]);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 size_t allpairs_eval_workspace_bytes(int64_t N, int D, int nthr) {

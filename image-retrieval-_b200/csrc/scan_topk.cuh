@@ -35,6 +35,30 @@ __global__ void prep_queries_kernel(const T* __restrict__ Q, int nq, int D, int 
   if (lane == 0) qnorm[warp] = sqrtf(ss);
 }
 
+// Same for the first *count rows of a device-side query list (fallback of the tensor path): row w of the output is
+// query list[w]; rows past the list up to the next multiple of 8 are zeroed, the rest is never read.
+template <typename T>
+__global__ void prep_queries_gather_kernel(const T* __restrict__ Q, const int* __restrict__ list, const int* __restrict__ count,
+                                           int D, int nq_pad, int D_pad, float* __restrict__ Qf, float* __restrict__ qnorm) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n = *count;
+  if (warp >= nq_pad || warp >= ((n + 7) & ~7)) return;
+  const int src = warp < n ? list[warp] : -1;
+  float ss = 0.f;
+  for (int d0 = 0; d0 < D_pad; d0 += 32) {
+    const int d = d0 + lane;
+    float v = 0.f;
+    if (src >= 0 && d < D) v = to_f32<T>(Q[int64_t(src) * D + d]);
+    if (d < D_pad) Qf[int64_t(warp) * D_pad + d] = v;
+    float p = v * v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    ss += p;
+  }
+  if (lane == 0) qnorm[warp] = sqrtf(ss);
+}
+
 // Warp-cooperative compaction of one query's candidate buffer: sort, keep the best k.
 template <int E>
 __device__ __noinline__ void compact_candidates(uint64_t* keys, int* cnt, uint64_t* thr, int k, int lane) {
@@ -114,6 +138,12 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = blockIdx.x % a.G;
   const int p = blockIdx.x / a.G;
+  int nq_eff = a.nq;
+  if (a.gate != nullptr) {                                 // fallback tier: serve only the list positions that exist
+    const int avail = *a.gate - a.gate_base;
+    if (g * TQ >= avail) return;
+    nq_eff = min(nq_eff, avail);
+  }
   int64_t row_begin = int64_t(p) * a.rows_per_part;
   const int64_t row_end = min(a.N, row_begin + a.rows_per_part);
   // evaluation mode: bins live where the key buffers would be; tiles whose rows are all <= the first query are skipped
@@ -326,7 +356,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
       for (int t = 0; t < TQ; ++t) {
         const int q = g * TQ + t;
         if constexpr (KIND == K_EVAL) {
-          if (valid && q < a.nq && grow > q) {
+          if (valid && q < nq_eff && grow > q) {
             // the five evaluation metrics of mi_analysis.py:183-189 from one pass (geometric_metrics.py:114-129)
             const float xn = sqrtf(xsq);
             float cs = 0.f;
@@ -353,7 +383,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
             }
           }
         } else
-        if (valid && q < a.nq) {
+        if (valid && q < nq_eff) {
           const float r = finish_rank<KIND>(acc[t], xsq, qn[t], a.mp);
           if (topk_mode) {
             const uint64_t key = make_key(r, uint32_t(grow));
@@ -396,7 +426,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
     __syncthreads();
     for (int t = warp; t < TQ; t += kScanThreads / 32) {
       const int q = g * TQ + t;
-      if (q >= a.nq) continue;
+      if (q >= nq_eff) continue;
       uint64_t* kb = keys_s + size_t(t) * a.sortn;
       if (a.sortn == 256) compact_candidates<8>(kb, &cnt_s[t], &thr_s[t], a.k, lane);
       else compact_candidates<16>(kb, &cnt_s[t], &thr_s[t], a.k, lane);

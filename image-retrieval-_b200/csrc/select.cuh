@@ -45,13 +45,17 @@ __device__ __forceinline__ void emit_topk(uint64_t (&r)[E], int lane, int k, con
 
 // One warp per query: stream P*k sorted-or-not keys through a 32*E-wide bitonic sorter, keeping
 // the best k between rounds.  Writes the reference-normalised score and the global index.
+// qmap / gate (both nullptr for a plain search): the launch finishes positions [0, min(nq, *gate - gate_base)) of a
+// device-side query list and writes row qmap[q] of the outputs (fallback of the tensor path).
 template <int E>
 __global__ void __launch_bounds__(128) finalize_topk_kernel(const uint64_t* __restrict__ partial, int nq, int64_t per_query,
                                                            int k, MetricParams mp, int64_t index_offset,
-                                                           float* __restrict__ out_score, int64_t* __restrict__ out_idx) {
+                                                           float* __restrict__ out_score, int64_t* __restrict__ out_idx,
+                                                           const int* __restrict__ qmap, const int* __restrict__ gate, int gate_base) {
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (q >= nq) return;
+  if (gate != nullptr && q >= *gate - gate_base) return;
   const uint64_t* src = partial + int64_t(q) * per_query;
   uint64_t r[E];
 #pragma unroll
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(128) finalize_topk_kernel(const uint64_t* __re
     warp_sort<E>(r, lane);
     kept = k;
   } while (pos < per_query);
-  emit_topk<E>(r, lane, k, mp, index_offset, out_score, out_idx, int64_t(q));
+  emit_topk<E>(r, lane, k, mp, index_offset, out_score, out_idx, qmap != nullptr ? int64_t(qmap[q]) : int64_t(q));
 }
 
 // Cross-shard merge: score/idx lists of R shards -> [nq, k] ordered by (score, global idx).
@@ -171,11 +175,12 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(int descending, const f
 }
 
 inline cudaError_t launch_finalize(const uint64_t* partial, int64_t nq, int64_t per_query, int k, const MetricParams& mp,
-                                   int64_t index_offset, float* out_score, int64_t* out_idx, cudaStream_t st) {
+                                   int64_t index_offset, float* out_score, int64_t* out_idx, cudaStream_t st,
+                                   const int* qmap = nullptr, const int* gate = nullptr, int gate_base = 0) {
   const int blocks = int(ceil_div64(nq, 4));
   ProfileScope ps(PT_FINALIZE, st);
-  if (k <= 128) finalize_topk_kernel<8><<<blocks, 128, 0, st>>>(partial, int(nq), per_query, k, mp, index_offset, out_score, out_idx);
-  else finalize_topk_kernel<16><<<blocks, 128, 0, st>>>(partial, int(nq), per_query, k, mp, index_offset, out_score, out_idx);
+  if (k <= 128) finalize_topk_kernel<8><<<blocks, 128, 0, st>>>(partial, int(nq), per_query, k, mp, index_offset, out_score, out_idx, qmap, gate, gate_base);
+  else finalize_topk_kernel<16><<<blocks, 128, 0, st>>>(partial, int(nq), per_query, k, mp, index_offset, out_score, out_idx, qmap, gate, gate_base);
   return cudaGetLastError();
 }
 

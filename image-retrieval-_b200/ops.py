@@ -9,8 +9,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (ANGLE, BF16, COS_DIST, COS_SIM, F32, FLAG_ABS_SCORE, FLAG_NO_RERANK, FLAG_NO_TENSOR, FLAG_RAW,
-                   HSV, L1, L2, LINF, MAG_DIFF, MAX_K, OPTIMIZED, RGB, B200IRError)
+from ._lib import (ANGLE, BF16, COS_DIST, COS_SIM, F32, FLAG_ABS_SCORE, FLAG_HAVE_INDEX, FLAG_NO_RERANK, FLAG_NO_TENSOR,
+                   FLAG_RAW, HSV, L1, L2, LINF, MAG_DIFF, MAX_K, OPTIMIZED, RGB, B200IRError)
 
 METRIC_IDS = {
     "l1": L1, "l1_distance": L1,
@@ -121,11 +121,55 @@ def row_sqnorms(X):
     return out
 
 
+class PreparedIndex:
+    """A static (N, D) store plus the per-store state the tensor-core searches reuse (b200ir_index_build: row norms,
+    max norm, bf16 hi / lo planes of an fp32 store).  Pass it to topk() in place of the matrix.  Rebuild it (or call
+    refresh()) after changing rows in place; the state is ignored by metrics / shapes without a tensor-core path."""
+
+    def __init__(self, X):
+        self.X = as_device_matrix(X)
+        self.state = None
+        self.refresh()
+
+    def refresh(self):
+        lib = _lib.load()
+        N, D = self.X.shape
+        need = lib.b200ir_index_bytes(_dtype_id(self.X), N, D) if N > 0 else 0
+        if need and self.X.data_ptr() % 16 == 0:
+            if self.state is None or self.state.numel() < need:
+                self.state = torch.empty(int(need), dtype=torch.uint8, device=self.X.device)
+            _lib.check(lib.b200ir_index_build(_dtype_id(self.X), _ptr(self.X), N, D, _ptr(self.state), self.state.numel(), _stream()),
+                       "index_build")
+        else:
+            self.state = None
+        return self
+
+    @property
+    def shape(self):
+        return self.X.shape
+
+    @property
+    def dtype(self):
+        return self.X.dtype
+
+    @property
+    def device(self):
+        return self.X.device
+
+
+def prepare_index(X):
+    return X if isinstance(X, PreparedIndex) else PreparedIndex(X)
+
+
 def topk(Q, X, metric, k, *, index_offset=0, normalized=True, abs_score=False, params=None, flags=0, out=None):
     """Fused distance + top-k.  Returns (scores (nq,k) fp32, indices (nq,k) int64) on the device,
-    best first, ties by ascending index; slots past N hold (+-inf, -1)."""
+    best first, ties by ascending index; slots past N hold (+-inf, -1).  X: matrix or PreparedIndex."""
     m = metric_id(metric)
-    X = as_device_matrix(X)
+    state = None
+    if isinstance(X, PreparedIndex):
+        X, state = X.X, X.state
+    else:
+        X = as_device_matrix(X)
     Q = as_device_matrix(Q, dtype=X.dtype)
     if Q.shape[1] != X.shape[1]:
         raise ValueError(f"dimension mismatch: queries {Q.shape[1]} vs database {X.shape[1]}")
@@ -143,12 +187,35 @@ def topk(Q, X, metric, k, *, index_offset=0, normalized=True, abs_score=False, p
         if scores.shape != (nq, k) or idx.shape != (nq, k) or scores.dtype != torch.float32 or idx.dtype != torch.int64 \
                 or not scores.is_contiguous() or not idx.is_contiguous():
             raise ValueError("out=(scores, idx) must be contiguous (nq, k) fp32 / int64 tensors")
-    need = lib.b200ir_topk_workspace_bytes(m, _dtype_id(X), nq, N, D, k, f)
-    ws = _workspace(need, X.device)
-    st = lib.b200ir_topk(m, _dtype_id(X), _ptr(Q), nq, _ptr(X), N, D, k, int(index_offset), f, _weights(params),
-                         _ptr(scores), _ptr(idx), _ptr(ws), ws.numel(), _stream())
+    if state is not None and nq > 0:
+        need = lib.b200ir_topk_workspace_bytes(m, _dtype_id(X), nq, N, D, k, f | FLAG_HAVE_INDEX)
+        ws = _workspace(need, X.device)
+        st = lib.b200ir_topk_indexed(m, _dtype_id(X), _ptr(Q), nq, _ptr(X), N, D, k, int(index_offset), f, _weights(params),
+                                     _ptr(scores), _ptr(idx), _ptr(state), state.numel(), _ptr(ws), ws.numel(), _stream())
+    else:
+        need = lib.b200ir_topk_workspace_bytes(m, _dtype_id(X), nq, N, D, k, f)
+        ws = _workspace(need, X.device)
+        st = lib.b200ir_topk(m, _dtype_id(X), _ptr(Q), nq, _ptr(X), N, D, k, int(index_offset), f, _weights(params),
+                             _ptr(scores), _ptr(idx), _ptr(ws), ws.numel(), _stream())
     _lib.check(st, "topk")
+    global _last_topk
+    _last_topk = (ws, m, _dtype_id(X), nq, N, D, k, f | (FLAG_HAVE_INDEX if state is not None and nq > 0 else 0))
     return scores, idx
+
+
+_last_topk = None
+
+
+def last_fallback_count():
+    """Queries of the most recent topk() call that failed the tensor path's exactness certificate and were re-done by
+    the exact scan (None when that call did not take the tensor path).  Synchronises; for tests and bench reports."""
+    if _last_topk is None:
+        return None
+    ws, m, dt, nq, N, D, k, f = _last_topk
+    off = _lib.load().b200ir_topk_fallback_counter_offset(m, dt, nq, N, D, k, f)
+    if off == ctypes.c_size_t(-1).value or nq == 0 or N == 0:
+        return None
+    return int(ws[off:off + 4].view(torch.int32).item())
 
 
 def pairwise(Q, X, metric, *, normalized=True, abs_score=False, params=None, flags=0):

@@ -34,6 +34,9 @@ def _round_up(a, b):
 
 class ShardedIndex:
     def __init__(self, local_rows, row_begin, group=None, local_topk=None, merge=None):
+        # default (CUDA) path: keep the per-shard search state (row norms, split planes) next to the rows
+        if local_topk is None and isinstance(local_rows, torch.Tensor) and local_rows.is_cuda:
+            local_rows = ops.prepare_index(local_rows)
         self.X = local_rows
         self.row_begin = int(row_begin)
         self.group = group
@@ -66,7 +69,7 @@ class ShardedIndex:
         """CUDA fast path: the local search writes scores and ids into ONE byte record, a single all-gather moves
         the records, and the merge kernel reads the receive buffer in place (no pack / unpack kernels)."""
         R = dist.get_world_size(self.group)
-        Qd = ops.as_device_matrix(Q, dtype=self.X.dtype if isinstance(self.X, torch.Tensor) else None)
+        Qd = ops.as_device_matrix(Q, dtype=self.X.dtype if isinstance(self.X, (torch.Tensor, ops.PreparedIndex)) else None)
         nq = Qd.shape[0]
         score_bytes = _round_up(nq * k * 4, 16)
         rec = _round_up(score_bytes + nq * k * 8, 16)

@@ -51,7 +51,8 @@ extern "C" {
 #define B200IR_FLAG_RAW        1   /* normalized=False for L1 / L2 (geometric_metrics.py:37,45) */
 #define B200IR_FLAG_ABS_SCORE  2   /* rank COS_SIM / OPTIMIZED by |score| (app_pipeline.py:167)  */
 #define B200IR_FLAG_NO_TENSOR  4   /* force the CUDA-core scan even where the tcgen05 path applies */
-#define B200IR_FLAG_NO_RERANK  8   /* tcgen05 path: skip the exact fp32 re-rank of the candidates */
+#define B200IR_FLAG_NO_RERANK  8   /* tcgen05 path, bf16 stores: skip the exact fp32 re-rank of the candidates */
+#define B200IR_FLAG_HAVE_INDEX 16  /* b200ir_topk_workspace_bytes: size the workspace for b200ir_topk_indexed */
 
 /* colour spaces of b200ir_histogram */
 #define B200IR_RGB 0
@@ -99,6 +100,34 @@ int b200ir_topk(int metric, int dtype, const void* Q, int64_t nq, const void* X,
                 int k, int64_t index_offset, int flags, const float* weights_host,
                 float* out_score, int64_t* out_idx,
                 void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Exactness of the tensor-core path.  L2 / cosine-family searches of bf16 and fp32 stores (D % 8 == 0, D <= 512,
+ * nq >= 32, N >= 1024, k <= 224) select kp > k candidates per query on tcgen05 (fp32 stores: three-term bf16 split),
+ * re-rank them with exact fp32 arithmetic on the original rows and CERTIFY the result: if a dropped row could still
+ * reach the k-th exact score within the proven error of the tensor-core pass, the query is re-done by the exact
+ * CUDA-core scan in the same call.  Results therefore equal the scan's; the int32 at this byte offset of the
+ * workspace holds the number of queries the last call re-did (device memory; (size_t)-1: the shape does not take the
+ * tensor-core path or B200IR_FLAG_NO_RERANK asked for the uncertified candidate scores).
+ */
+size_t b200ir_topk_fallback_counter_offset(int metric, int dtype, int64_t nq, int64_t N, int D, int k, int flags);
+
+/*
+ * Prepared per-store state for repeated searches of a static store (the store plays the part of
+ * app_pipeline.py:18 `self.embeddings` / the Milvus collection of ImageEmbeddingSystem.py:41-61, which the
+ * reference also builds once and searches many times): row norms (the reference recomputes |e| for every pair,
+ * app_pipeline.py:161-163), the largest norm, and for fp32 stores the two bf16 planes of the error-compensated
+ * split the tensor-core pass multiplies.  b200ir_index_bytes() is 0 when the shape has no tensor-core path
+ * (D % 8 != 0 or D > 512): use plain b200ir_topk then.  The index is only valid while X is unchanged.
+ * b200ir_topk_indexed == b200ir_topk with that state supplied instead of being rebuilt inside the workspace on
+ * every call; results are identical.  Metrics without a tensor-core path ignore the index.
+ */
+size_t b200ir_index_bytes(int dtype, int64_t N, int D);
+int b200ir_index_build(int dtype, const void* X, int64_t N, int D, void* index, size_t index_bytes, void* stream);
+int b200ir_topk_indexed(int metric, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D,
+                        int k, int64_t index_offset, int flags, const float* weights_host,
+                        float* out_score, int64_t* out_idx, const void* index, size_t index_bytes,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Full (nq, N) metric matrix, same arithmetic as b200ir_topk's CUDA-core scan.

@@ -1,0 +1,182 @@
+"""GPU parity of the tcgen05 path on fp32 stores (three-term bf16 split + exact fp32 re-rank + exactness
+certificate with exact-scan fallback) against the fp64 oracle, and of the certificate itself on adversarial
+near-tie / duplicate data for both element types.  Reference semantics: geometric_metrics.py:12-18 (cosine),
+:42-47 (L2), app_pipeline.py:156-172 (scan + stable sort + slice).  Run with -m gpu."""
+import numpy as np
+import pytest
+
+from oracle import metrics as OM
+from oracle import search as OS
+from oracle import synth
+from parity import check_topk
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from image_retrieval_b200 import ops as o
+    o.device()
+    return o
+
+
+def _tol(metric):
+    if metric in ("cosine_similarity", "cosine_distance"):
+        return dict(rtol=1e-5, atol=2e-6)
+    if metric == "angular_distance":
+        return dict(rtol=1e-5, atol=1e-5 * np.pi)
+    return dict(rtol=1e-5, atol=1e-30)
+
+
+@pytest.mark.parametrize("metric", ["cosine_similarity", "cosine_distance", "angular_distance", "l2"])
+@pytest.mark.parametrize("nq,N,D,k", [(64, 4096, 512, 10), (300, 50_000, 512, 100), (129, 20_001, 256, 100),
+                                      (40, 3000, 96, 5), (200, 9000, 40, 224)])
+def test_fp32_tensor_path_vs_oracle(ops, metric, nq, N, D, k):
+    Q = synth.gaussian(nq, D, 11)
+    X = synth.gaussian(N, D, 12)
+    X[7] = 0                                   # zero row: cos := 0 (geometric_metrics.py:16-17)
+    X[11] = Q[3]                               # exact self match
+    s, i = ops.topk(Q, X, metric, k)
+    assert ops.last_fallback_count() is not None, "fp32 store did not take the tensor-core path"
+    truth = OM.pairwise_f64(Q, X, metric)
+    disputed = check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, k, OM.DESCENDING[metric], **_tol(metric))
+    assert disputed <= max(1, nq * k // 200), f"{disputed} disputed ranks"
+    assert i[3, 0].item() == 11
+
+
+def test_fp32_tensor_equals_exact_scan(ops):
+    """Same index lists as the CUDA-core scan (both re-rank / rank with direct fp32 arithmetic); scores within 1e-6."""
+    Q = synth.gaussian(96, 512, 21)
+    X = synth.gaussian(30_000, 512, 22)
+    for metric in ("cosine_similarity", "l2"):
+        s1, i1 = ops.topk(Q, X, metric, 50)
+        s2, i2 = ops.topk(Q, X, metric, 50, flags=ops.FLAG_NO_TENSOR)
+        same = (i1 == i2).float().mean().item()
+        assert same > 0.999, (metric, same)                      # fp32 summation order may swap a rounding-level near-tie
+        np.testing.assert_allclose(s1.cpu().numpy(), s2.cpu().numpy(), rtol=2e-6, atol=1e-6)
+
+
+def test_fp32_prepared_index_same_results(ops):
+    import torch
+    Q = torch.from_numpy(synth.gaussian(64, 512, 31)).cuda()
+    X = torch.from_numpy(synth.gaussian(10_000, 512, 32)).cuda()
+    idx = ops.prepare_index(X)
+    assert idx.state is not None
+    for metric in ("cosine_similarity", "l2", "angular_distance"):
+        s1, i1 = ops.topk(Q, X, metric, 20)
+        s2, i2 = ops.topk(Q, idx, metric, 20)
+        assert torch.equal(i1, i2) and torch.equal(s1, s2), metric
+    # metrics without a tensor-core path ignore the state
+    s1, i1 = ops.topk(Q, X, "l1", 20)
+    s2, i2 = ops.topk(Q, idx, "l1", 20)
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+    Xb = X.bfloat16()
+    idb = ops.prepare_index(Xb)
+    s1, i1 = ops.topk(Q.bfloat16(), Xb, "cosine_similarity", 20)
+    s2, i2 = ops.topk(Q.bfloat16(), idb, "cosine_similarity", 20)
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+
+
+def test_split_error_below_certificate_bound(ops):
+    """The uncertified candidate scores (FLAG_NO_RERANK) of an fp32 store differ from the exact cosine by far less
+    than the u_eff = 2^-14 the certificate assumes (measured: ~1e-6)."""
+    Q = synth.gaussian(64, 512, 41)
+    X = synth.gaussian(8192, 512, 42)
+    s, i = ops.topk(Q, X, "cosine_similarity", 50, flags=ops.FLAG_NO_RERANK)
+    truth = OM.pairwise_f64(Q, X, "cosine_similarity")
+    exact = np.take_along_axis(truth, i.cpu().numpy(), axis=1)
+    err = np.abs(s.cpu().numpy() - exact).max()
+    assert err < 2.0 ** -14 / 4, err
+    truth_b = OM.pairwise_f64(OM.bf16_round(Q), OM.bf16_round(X), "cosine_similarity")
+    import torch
+    sb, ib = ops.topk(torch.from_numpy(OM.bf16_round(Q)).cuda().bfloat16(), torch.from_numpy(OM.bf16_round(X)).cuda().bfloat16(),
+                      "cosine_similarity", 50, flags=ops.FLAG_NO_RERANK)
+    errb = np.abs(sb.cpu().numpy() - np.take_along_axis(truth_b, ib.cpu().numpy(), axis=1)).max()
+    assert errb < 2.0 ** -16 / 4, errb
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_certificate_near_ties_fall_back_to_exact_scan(ops, bf16):
+    """Adversarial store: for every query, 64 rows whose scores sit within ~1e-7 of each other straddle rank k, far
+    more than the k' - k margin of the candidate pass.  The certificate must fail for those queries and the exact scan
+    must produce the answer: identical to the forced CUDA-core scan, and consistent with the fp64 oracle."""
+    import torch
+    rng = np.random.default_rng(7)
+    nq, N, D, k = 64, 6000, 256, 10
+    Q = rng.standard_normal((nq, D)).astype(np.float32)
+    X = rng.standard_normal((N, D)).astype(np.float32) * 0.5
+    for q in range(nq):                                           # 5 clear winners, then a cloud of 64 near-ties
+        for j in range(5):
+            X[100 * q % N + j] = Q[q] * (1.0 + 0.01 * j) + rng.standard_normal(D).astype(np.float32) * 0.05 * (j + 1)
+    cloud = rng.choice(np.arange(N - 700, N), 64, replace=False)
+    base = Q.mean(axis=0)
+    for c in cloud:
+        X[c] = base + rng.standard_normal(D).astype(np.float32) * 1e-7
+    if bf16:
+        Q, X = OM.bf16_round(Q), OM.bf16_round(X)
+        for c in cloud[1:]:
+            X[c] = X[cloud[0]]                                    # bf16 cannot express 1e-7 steps: exact duplicates instead
+        Qd, Xd = torch.from_numpy(Q).cuda().bfloat16(), torch.from_numpy(X).cuda().bfloat16()
+    else:
+        Qd, Xd = torch.from_numpy(Q).cuda(), torch.from_numpy(X).cuda()
+    for metric in ("cosine_similarity", "l2"):
+        s1, i1 = ops.topk(Qd, Xd, metric, k)
+        fb = ops.last_fallback_count()
+        s2, i2 = ops.topk(Qd, Xd, metric, k, flags=ops.FLAG_NO_TENSOR)
+        truth = OM.pairwise_f64(Q, X, metric)
+        order = np.argsort(-truth if OM.DESCENDING[metric] else truth, axis=1, kind="stable")[:, :k]
+        touched = sum(1 for q in range(nq) if np.isin(order[q], cloud).any())
+        if touched:
+            assert fb is not None and fb >= touched // 2, (metric, fb, touched)
+        assert torch.equal(i1, i2), metric
+        np.testing.assert_allclose(s1.cpu().numpy(), s2.cpu().numpy(), rtol=2e-6, atol=1e-6)
+        check_topk(s1.cpu().numpy(), i1.cpu().numpy(), truth, k, OM.DESCENDING[metric], **_tol(metric))
+
+
+def test_histogram_embeddings_fp32_l2_exact_indices(ops):
+    """Config-1 shape in miniature: integer histogram embeddings with self matches and duplicates, L2 top-10 through
+    the tensor path: index lists equal the oracle's stable sort exactly."""
+    from oracle import histogram as OH
+    imgs = synth.images_palette(1200, 32, 32, 5)
+    X = OH.histogram(imgs).astype(np.float32)
+    X[600:650] = X[0:50]                                          # duplicates: ties resolve to the lower index
+    Q = X[:64].copy()
+    s, i = ops.topk(Q, X, "l2", 10)
+    assert ops.last_fallback_count() is not None
+    truth = OM.pairwise_f64(Q, X, "l2")
+    tv, ti = OS.topk(truth, 10, False)
+    assert np.array_equal(i.cpu().numpy(), ti)
+    np.testing.assert_allclose(s.cpu().numpy(), tv, rtol=1e-5, atol=1e-30)
+
+
+def test_full_size_fp32_tensor_path(ops):
+    """north_star size for fp32 stores: 10k queries x 1M x 512 fp32, cosine and L2 top-100 on tcgen05; a 24-query
+    sample is checked against the fp64 oracle, the whole batch through size-independent properties."""
+    import torch
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev)
+    g.manual_seed(2101)
+    N, D, nq, k = 1_000_000, 512, 10_000, 100
+    X = torch.randn((N, D), generator=g, device=dev)
+    X /= X.norm(dim=1, keepdim=True)
+    Q = torch.randn((nq, D), generator=g, device=dev)
+    Q /= Q.norm(dim=1, keepdim=True)
+    X[123_456] = Q[17]
+    idx = ops.prepare_index(X)
+    Xh = X.cpu().numpy()
+    sample = np.arange(0, nq, nq // 24)[:24]
+    for metric in ("cosine_similarity", "l2"):
+        s, i = ops.topk(Q, idx, metric, k)
+        fb = ops.last_fallback_count()
+        assert fb is not None and fb <= nq // 100, fb
+        s_h, i_h = s.cpu().numpy(), i.cpu().numpy()
+        key = -s_h if metric == "cosine_similarity" else s_h
+        assert np.all(np.diff(key, axis=1) >= 0)                              # sorted best-first
+        assert np.all((i_h >= 0) & (i_h < N))
+        assert all(len(set(r.tolist())) == k for r in i_h[::97])             # no duplicates
+        assert i_h[17, 0] == 123_456
+        truth = OM.pairwise_f64(Q[sample].cpu().numpy(), Xh, metric)
+        disputed = check_topk(s_h[sample], i_h[sample], truth, k, OM.DESCENDING[metric], **_tol(metric))
+        assert disputed <= 12, disputed
