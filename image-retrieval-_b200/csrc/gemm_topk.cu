@@ -441,13 +441,21 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_units = a.num_qgroups * a.P;
+  // Unit order.  Partition-major (default): all clusters stream the same database range together, so a tile is read
+  // from DRAM once per round and served from L2 to everybody else.  Query-major (B200IR_GEMM_OPT bit 2: the P partitions
+  // of a query group run at the same time and pool their candidates through the shared thresholds sooner) was measured
+  // 39 % SLOWER on the headline shape (12.28 vs 8.82 ms, also at k = 10): P concurrent streams at a fixed 91 MB stride
+  // lose the L2 sharing and more than eat the shorter cold phase.  Kept as a switch for the record.
+  const bool part_major = (a.opt & 4) == 0;
+  auto unit_qgroup = [&](int unit) { return part_major ? unit % a.num_qgroups : unit / a.P; };
+  auto unit_part = [&](int unit) { return part_major ? unit / a.num_qgroups : unit % a.P; };
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       uint32_t kiter = 0, uiter = 0, titer = 0;
       for (int unit = cluster_id; unit < num_units; unit += nclusters, ++uiter) {
-        const int qt = (unit % a.num_qgroups) * NCTA + int(rank), p = unit / a.num_qgroups;
+        const int qt = unit_qgroup(unit) * NCTA + int(rank), p = unit_part(unit);
         long long t0 = DBG_T0();
         mbar_wait(A_EMPTY, (uiter & 1) ^ 1);                   // previous unit's MMAs are done with A
         DBG_ADD(1, t0);
@@ -500,7 +508,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // ===================== MMA issuer (leader CTA only) =====================
       uint32_t kiter = 0, titer = 0, uiter = 0;
       for (int unit = cluster_id; unit < num_units; unit += nclusters, ++uiter) {
-        const int p = unit / a.num_qgroups;
+        const int p = unit_part(unit);
         const int tile0 = p * a.tiles_per_part;
         const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
         if (a.dbg) {                                             // MMA-issue time stamps per round: slot 15 = round 0, 11 = later
@@ -635,7 +643,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int dbg_round = -1;
     for (int unit = cluster_id; unit < num_units; unit += nclusters) {
       ++dbg_round;
-      const int qt = (unit % a.num_qgroups) * NCTA + int(rank), p = unit / a.num_qgroups;
+      const int qt = unit_qgroup(unit) * NCTA + int(rank), p = unit_part(unit);
       const int q = qt * BM + row;
       thr = q < a.nq ? -INFINITY : INFINITY;                   // padding rows of the last query tile accept nothing
       cnt = 0;                                                 // my end of the list (register; published at every barrier)
