@@ -3,7 +3,11 @@
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one JSON line on rank 0)
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU path, same metric
-    python bench.py --workload l1_scan|linf_scan|l2_fp32|histogram|config1 ...   # other s8(d) rows
+    python bench.py --workload l1_scan|linf_scan|l2_fp32|cos_tensor_fp32|histogram|config1|config5|... # one s8(d) row
+
+The default line also carries `side` (the other s8(d) rows, N = 1 only, each timed for >= 0.25 s so the clock sampler
+sees it), `strong` (BASELINE configs[3]: a 10M x 512 store row-sharded over the N ranks, cosine + L1) and `parity`
+(at N > 1 against a distributed oracle: every rank's NumPy top-k of its own shard, merged on rank 0).
 
 Headline workload (BASELINE.json configs[1]): cosine top-100, 10k-query bf16 batch against a
 1M x 512 bf16 database per GPU.  One "step" = one pass of the hot path over one query batch.
@@ -149,14 +153,15 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------ CPU legs
-def cpu_port_baseline(Qh, Xh, k, budget_s=20.0):
-    """Vectorised NumPy port (oracle.search.topk_search: sgemm + stable argsort) on a bounded sample of the
-    query batch against the FULL database, all host cores via BLAS."""
+def cpu_port_baseline(Qh, Xh, k, budget_s=6.0):
+    """Vectorised NumPy port (oracle.search.topk_search: sgemm + FULL stable argsort, the reference's list.sort semantics)
+    on a bounded sample of the query batch against the FULL database, all host cores via BLAS.  Also returns the
+    (values, indices) of the first 16 queries: the parity spot-check of the timed GPU result."""
     import numpy as np
     from oracle import search as OS
     nq = 16
     t0 = time.perf_counter()
-    _first_v, first_i = OS.topk_search(Qh[:nq], Xh, "cosine_similarity", k, dtype=np.float32)
+    first_v, first_i = OS.topk_search(Qh[:nq], Xh, "cosine_similarity", k, dtype=np.float32)
     dt = time.perf_counter() - t0
     done = nq
     if dt < budget_s / 3:
@@ -167,7 +172,37 @@ def cpu_port_baseline(Qh, Xh, k, budget_s=20.0):
         done = nq2
     return {"value": done / dt, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"{done} of {len(Qh)} queries vs the full {Xh.shape[0]}x{Xh.shape[1]} fp32 database, "
-                      f"NumPy sgemm + stable argsort (oracle.search.topk_search), {dt:.1f} s"}, first_i
+                      f"NumPy sgemm + stable argsort (oracle.search.topk_search), {dt:.1f} s"}, first_v, first_i
+
+
+def cpu_torch_baseline(Qh, Xh, k, budget_s=12.0):
+    """Best-effort vectorised CPU path of BASELINE.md section 3.2: row-normalised torch.mm + torch.topk on all host
+    cores, 64-query batches against the FULL database (row norms precomputed once, like our prepared index)."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    X = torch.from_numpy(Xh)
+    Q = torch.from_numpy(Qh)
+    rx = 1.0 / X.norm(dim=1).clamp_min(1e-30)
+    nq = 64
+
+    def batch(b):
+        q = Q[b * nq % len(Q):][:nq]
+        sc = torch.mm(q, X.t())
+        sc *= (1.0 / q.norm(dim=1).clamp_min(1e-30))[:, None]
+        sc *= rx[None, :]
+        return torch.topk(sc, k, dim=1)
+    batch(0)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        batch(n)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 40:
+            break
+    return {"value": n * nq / dt, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} batches of {nq} queries vs the full {Xh.shape[0]}x{Xh.shape[1]} fp32 database, torch.mm + "
+                      f"torch.topk (BASELINE.md 3.2), {torch.get_num_threads()} threads, {dt:.1f} s"}
 
 
 def _ref_loop_worker(args):
@@ -244,6 +279,120 @@ def headline_config(n_gpus):
 
 
 # ------------------------------------------------------------------------------------ our arm
+def roofline_tensor(pk, kern_name, kern_ms, flops, kernels_ms=None, traffic=None):
+    """Tensor-pipe roofline of one launch: `frac` is against the BURST cuBLAS figure (a 10-20 ms kernel inside a
+    sub-second run is in the burst regime: clocks near max, power below the cap); `frac_sustained` against the
+    seconds-long figure, both from MEASURED_PEAKS.json."""
+    burst = pk.get("bf16_tflops", PEAKS_FALLBACK["bf16_tflops"])
+    sust = pk.get("bf16_tflops_sustained", PEAKS_FALLBACK["bf16_tflops_sustained"])
+    ach = flops / (kern_ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": kern_name, "achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst,
+            "frac_burst": ach / burst, "frac_sustained": ach / sust, "peak_sustained": sust, "traffic": traffic,
+            "kernel_ms": kern_ms, "kernels_ms": kernels_ms, "algorithmic_flops_per_launch": flops,
+            "peak_source": pk["_source"] + ": bf16_tflops (burst) for `frac`, bf16_tflops_sustained for `frac_sustained`"}
+
+
+def read_kernel_ms(lib, tags):
+    import ctypes
+    out = {}
+    for tag, name in tags:
+        ms, n = ctypes.c_float(0), ctypes.c_int(0)
+        lib.b200ir_profile_read(tag, ctypes.byref(ms), ctypes.byref(n))
+        if n.value:
+            out[name] = ms.value / n.value
+    return out
+
+
+def drain_profile(lib):
+    """Drop the events of every kernel class (a previous workload may have recorded classes it never read)."""
+    import ctypes
+    for tag in range(16):
+        ms, n = ctypes.c_float(0), ctypes.c_int(0)
+        if lib.b200ir_profile_read(tag, ctypes.byref(ms), ctypes.byref(n)) != 0:
+            break
+
+
+KERNEL_TAGS = ((2, "gemm_topk(tcgen05)"), (1, "scan_topk(cuda-core)"), (3, "finalize"), (4, "rerank"), (0, "prep"), (5, "merge"))
+
+
+def distributed_oracle_parity(np, torch, dist, world, rank, dev, Q, X, row_begin, got_i, k, nq=16):
+    """Parity of the sharded result at any N: every rank runs the NumPy port (oracle) for the first `nq` queries on
+    ITS shard, the per-shard lists are gathered and merged on the host with the reference's (score, index) order, and
+    rank 0 compares the merged oracle with the GPU result of the timed step."""
+    from oracle import search as OS
+    v, i = OS.topk_search(Q[:nq].float().cpu().numpy(), X.float().cpu().numpy(), "cosine_similarity", k, dtype=np.float32)
+    i = i + row_begin
+    if world > 1:
+        tv = torch.from_numpy(np.ascontiguousarray(v)).to(dev)
+        ti = torch.from_numpy(np.ascontiguousarray(i)).to(dev)
+        gv = [torch.empty_like(tv) for _ in range(world)]
+        gi = [torch.empty_like(ti) for _ in range(world)]
+        dist.all_gather(gv, tv)
+        dist.all_gather(gi, ti)
+        v, i = OS.merge_topk(np.stack([t.cpu().numpy() for t in gv]), np.stack([t.cpu().numpy() for t in gi]), k, True)
+    if rank != 0:
+        return None
+    got = got_i[:nq].cpu().numpy()
+    return {"queries_checked": int(nq), "shards": world,
+            "index_sets_equal": bool(all(set(a_) == set(b_) for a_, b_ in zip(got, i))),
+            "ranks_equal_frac": float((got == i).mean()),
+            "note": "GPU (tcgen05 candidates + exact fp32 re-rank + certificate) vs the NumPy fp32 port run per shard and merged "
+                    "with (score, index) order; rank swaps only between fp32-equal scores"}
+
+
+def strong_config4(args, torch, dist, world, rank, local, dev):
+    """BASELINE configs[3] as a STRONG-scaling record: a 10M x 512 store row-sharded over the ranks (total fixed),
+    one all-gather + merge per search.  Cosine top-100 of 10k bf16 queries (tensor path) and L1 top-10 of 8 fp32
+    queries (HBM scan).  Max over ranks, CUDA events, clocks sampled during each timed loop."""
+    from image_retrieval_b200.sharded import ShardedIndex, shard_range
+    total = args.strong_rows
+    b, e = shard_range(total, world, rank)
+    n_local = e - b
+    res = {"db_rows_total": total, "rows_per_gpu": n_local, "scaling": "strong"}
+
+    def timed(fn, steps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), clk.summary()
+
+    Xb = make_unit_rows(torch, n_local, DIM, 4001 + rank, dev, torch.bfloat16)
+    Qb = make_unit_rows(torch, NQ, DIM, 4002, dev, torch.bfloat16)
+    idx = ShardedIndex(Xb, b)
+    ms, clocks = timed(lambda: idx.topk(Qb, "cosine_similarity", TOPK), max(5, int(300 * world / 100)))
+    res["cosine_top100_bf16"] = {"queries": NQ, "ms": ms, "queries_per_s": NQ / (ms * 1e-3), "clocks": clocks,
+                                 "tflops_per_gpu": 2.0 * NQ * n_local * DIM / (ms * 1e-3) / 1e12}
+    del Xb, idx
+    torch.cuda.empty_cache()
+    Xf = make_unit_rows(torch, n_local, DIM, 4001 + rank, dev, torch.float32)
+    Qf = make_unit_rows(torch, 8, DIM, 4003, dev, torch.float32)
+    idx = ShardedIndex(Xf, b, prepare=False)
+    ms, clocks = timed(lambda: idx.topk(Qf, "l1", 10), max(20, int(60 * world)))
+    res["l1_top10_fp32"] = {"queries": 8, "ms": ms, "queries_per_s": 8 / (ms * 1e-3), "clocks": clocks,
+                            "hbm_GBps_per_gpu": n_local * DIM * 4 / (ms * 1e-3) / 1e9}
+    del Xf, idx
+    torch.cuda.empty_cache()
+    return res
+
+
+SIDE_ROWS = (("l1_scan", dict(dim=512, queries=1)), ("l1_scan", dict(dim=512, queries=8)), ("linf_scan", dict(dim=512, queries=8)),
+             ("l1_scan", dict(dim=2048, queries=8)), ("l1_scan", dict(dim=512, queries=1024)), ("cos_tensor_fp32", {}), ("l2_tensor_fp32", {}),
+             ("histogram", {}), ("histogram", dict(hsv=True)), ("resize", {}), ("config1", {}), ("config5", {}), ("pairs", {}))
+
+
 def run_headline(args):
     import numpy as np
     import torch
@@ -262,9 +411,12 @@ def run_headline(args):
     X = make_unit_rows(torch, ROWS_PER_GPU, DIM, 2001 + rank, dev, torch.bfloat16)
     Q = make_unit_rows(torch, NQ, DIM, 2002, dev, torch.bfloat16)
     Q_host = Q.cpu().pin_memory()
-    out_s_host = torch.empty((NQ, TOPK), dtype=torch.float32).pin_memory()
-    out_i_host = torch.empty((NQ, TOPK), dtype=torch.int64).pin_memory()
-    index = ShardedIndex(X, rank * ROWS_PER_GPU)
+    # end to end every rank hands ITS slice of the query batch to its host consumer (the ranks hold identical results
+    # after the merge): together the R ranks deliver each result row to the host exactly once
+    q0, q1 = rank * NQ // world, (rank + 1) * NQ // world
+    out_s_host = torch.empty((q1 - q0, TOPK), dtype=torch.float32).pin_memory()
+    out_i_host = torch.empty((q1 - q0, TOPK), dtype=torch.int64).pin_memory()
+    index = ShardedIndex(X, rank * ROWS_PER_GPU)          # per-store search state (row norms) is built here, once
     flags = ops.FLAG_NO_TENSOR if args.no_tensor else 0
 
     def step():
@@ -274,8 +426,8 @@ def run_headline(args):
         # the call a user makes, host buffers on both sides: pinned queries -> device, search, results -> pinned host
         q = Q_host.to(dev, non_blocking=True)
         s, i = index.topk(q, "cosine_similarity", TOPK, flags=flags)
-        out_s_host.copy_(s, non_blocking=True)
-        out_i_host.copy_(i, non_blocking=True)
+        out_s_host.copy_(s[q0:q1], non_blocking=True)
+        out_i_host.copy_(i[q0:q1], non_blocking=True)
         torch.cuda.current_stream().synchronize()          # results are usable on the host after every step
         return out_s_host, out_i_host
 
@@ -307,21 +459,28 @@ def run_headline(args):
     with ClockSampler(local) as clk:
         ms_step, (s_dev, i_dev) = timed(step, args.steps)
     launches = lib.b200ir_launch_count() - launches0
+    fallback_queries = ops.last_fallback_count()
     ms_e2e, _ = timed(step_e2e, max(2, min(args.steps, 5)))
 
     # dominant-kernel duration on its launching stream (separate pass; events perturb nothing else)
-    import ctypes
+    drain_profile(lib)
     lib.b200ir_profile_enable(1)
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-    kern = {}
-    for tag, name in ((2, "gemm_topk(tcgen05)"), (1, "scan_topk(cuda-core)"), (3, "finalize"), (4, "rerank"), (0, "prep"), (5, "merge")):
-        ms, n = ctypes.c_float(0), ctypes.c_int(0)
-        lib.b200ir_profile_read(tag, ctypes.byref(ms), ctypes.byref(n))
-        if n.value:
-            kern[name] = ms.value / n.value
+    kern = read_kernel_ms(lib, KERNEL_TAGS)
     lib.b200ir_profile_enable(0)
+
+    # parity of the timed result, at every N (the oracle runs here and in the CPU leg only)
+    parity = None
+    if not args.no_cpu:
+        parity = distributed_oracle_parity(np, torch, dist, world, rank, dev, Q, X, rank * ROWS_PER_GPU, i_dev, TOPK)
+    strong = None
+    if not args.no_strong:
+        del index, X
+        torch.cuda.empty_cache()
+        strong = strong_config4(args, torch, dist, world, rank, local, dev)
+        X = make_unit_rows(torch, ROWS_PER_GPU, DIM, 2001 + rank, dev, torch.bfloat16)
 
     if rank != 0:
         if world > 1:
@@ -334,8 +493,6 @@ def run_headline(args):
     flops = 2.0 * NQ * ROWS_PER_GPU * DIM
     roofline = None
     if dom:
-        peak = pk.get("bf16_tflops_sustained", PEAKS_FALLBACK["bf16_tflops_sustained"])
-        ach = flops / (kern[dom] * 1e-3) / 1e12
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -344,33 +501,45 @@ def run_headline(args):
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]      # measured under ncu, per launch
         except Exception:  # noqa: BLE001
             pass
-        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": traffic, "kernel_ms": kern[dom], "kernels_ms": kern,
-                    "algorithmic_flops_per_launch": flops, "peak_source": pk["_source"] + ", sustained bf16 (kernel timed inside back-to-back steps)"}
+        roofline = roofline_tensor(pk, dom, kern[dom], flops, kern, traffic)
 
-    # CPU leg (the only place the oracle runs in this arm): the vectorised port is timed on a bounded query sample, and
-    # its answer for the first 16 queries doubles as a parity spot-check of the timed GPU result
-    cpu, parity = None, None
+    # CPU legs: the best-effort vectorised path (torch.mm + topk) is the reported cpu_baseline; the NumPy
+    # port with the reference's full stable sort rides along
+    cpu, cpu_port = None, None
     if not args.no_cpu:
-        cpu, ref_i = cpu_port_baseline(Q.float().cpu().numpy(), X.float().cpu().numpy(), TOPK)
-        if world == 1:
-            got = i_dev[:len(ref_i)].cpu().numpy()
-            parity = {"queries_checked": int(len(ref_i)),
-                      "index_sets_equal": bool(all(set(a_) == set(b_) for a_, b_ in zip(got, ref_i))),
-                      "ranks_equal_frac": float((got == ref_i).mean()),
-                      "note": "GPU (fp32 re-rank) vs NumPy fp32 port; rank swaps only between fp32-equal scores"}
+        Xh, Qh = X.float().cpu().numpy(), Q.float().cpu().numpy()
+        cpu = cpu_torch_baseline(Qh, Xh, TOPK)
+        cpu_port, _v, _i = cpu_port_baseline(Qh, Xh, TOPK)
+    side = None
+    if world == 1 and not args.no_side:
+        del X
+        torch.cuda.empty_cache()
+        side = {}
+        for w, kw in SIDE_ROWS:
+            a2 = argparse.Namespace(**{**vars(args), "workload": w, "no_cpu": True, "rows": 0, "dim": 0, "queries": 0, "k": 0,
+                                       "hsv": False, **kw})
+            try:
+                r = measure_side(a2)
+                key = w + "".join(f"_{k_}{v_}" for k_, v_ in kw.items())
+                side[key] = {k_: r[k_] for k_ in ("metric", "value", "unit", "ms_per_step", "steps", "gpu_launches", "clocks", "roofline",
+                                                 "config") if k_ in r}
+            except Exception as ex:  # noqa: BLE001
+                side[w] = {"error": repr(ex)[:300]}
+            torch.cuda.empty_cache()
     total_rows = ROWS_PER_GPU * world
     scale = total_rows / 1e6
     h2d = NQ * DIM * 2
-    d2h = NQ * TOPK * (4 + 8)
+    d2h = (q1 - q0) * TOPK * (4 + 8)
     line = {
         "metric": METRIC, "value": NQ * scale / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 inputs, fp32 accumulate", "data": "synthetic (row-normalised N(0,1), seeded, generated on device)",
         "config": headline_config(world),
         "e2e": {"value": NQ * scale / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e, "note": "pinned host query batch -> device, fused scan, (scores, ids) -> host; database resident in HBM"},
-        "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+                "ms_per_step": ms_e2e, "note": "per rank: pinned host query batch -> device, fused scan (+ all-gather + merge), this rank's "
+                                               "1/N slice of the (scores, ids) -> pinned host; database resident in HBM"},
+        "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_port": cpu_port,
+        "parity": parity, "fallback_queries_per_step": fallback_queries, "strong": strong, "side": side,
         "path": "cuda-core scan" if (args.no_tensor or "gemm_topk(tcgen05)" not in kern) else "tcgen05 gemm + fused top-k",
     }
     print(json.dumps(line))
@@ -398,8 +567,13 @@ def side_cpu_baseline(kind, unit, fn, units_per_call, sample, budget_s=6.0):
 
 
 def run_side(args):
-    """Secondary s8(d) workloads (single GPU): HBM-bound scans, exact fp32 L2, histograms."""
-    import ctypes
+    print(json.dumps(measure_side(args)))
+    return 0
+
+
+def measure_side(args):
+    """Secondary s8(d) workloads (single GPU): HBM-bound scans, the fp32 tensor path, histograms, evaluation.  Returns
+    the JSON line as a dict.  Every timed loop runs for at least ~0.25 s so that the 20 ms clock sampler sees it."""
     import numpy as np
     import torch
     from image_retrieval_b200 import _lib, ops
@@ -409,28 +583,42 @@ def run_side(args):
     pk = peaks()
     w = args.workload
 
-    def time_fn(fn, tag):
-        for _ in range(max(args.warmup, 3)):
+    def time_fn(fn, tags):
+        # calibrate: one call, then enough warm-ups / steps for a >= 0.25 s timed loop (>= 5 clock samples at 20 ms)
+        fn()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(); fn(); c1.record(); torch.cuda.synchronize()
+        est = max(c0.elapsed_time(c1), 1e-3)
+        warm = max(1, min(max(args.warmup, 3), int(300 / est)))
+        steps = int(max(1, min(5000, max(args.steps if est < 50 else 1, 250 / est))))
+        for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         n0 = lib.b200ir_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(0) as clk:
             e0.record()
-            for _ in range(args.steps):
+            for _ in range(steps):
                 fn()
             e1.record()
             torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
-        launches = lib.b200ir_launch_count() - n0
+        ms = e0.elapsed_time(e1) / steps
+        launches = (lib.b200ir_launch_count() - n0) / steps
+        drain_profile(lib)
         lib.b200ir_profile_enable(1)
-        for _ in range(3):
+        for _ in range(3 if est < 100 else 1):
             fn()
         torch.cuda.synchronize()
-        kms, n = ctypes.c_float(0), ctypes.c_int(0)
-        lib.b200ir_profile_read(tag, ctypes.byref(kms), ctypes.byref(n))
+        kms = read_kernel_ms(lib, tags)
         lib.b200ir_profile_enable(0)
-        return ms, kms.value / max(n.value, 1), launches, clk.summary()
+        return ms, kms, launches, clk.summary(), steps
+
+    def hbm_roofline(kernel, kms, bytes_alg):
+        ach = bytes_alg / (kms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "frac_of_nominal_8TBs": ach / 8000.0, "traffic": None, "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_alg,
+                "peak_source": pk["_source"] + ": hbm_gbs (copy bandwidth, read + write)"}
 
     if w in ("l1_scan", "linf_scan", "l2_fp32", "cos_fp32"):
         D = args.dim or 2048
@@ -441,48 +629,70 @@ def run_side(args):
         g = torch.Generator(device=dev); g.manual_seed(3001)
         X = torch.relu(torch.randn((N, D), generator=g, device=dev))
         Q = torch.relu(torch.randn((nq, D), generator=g, device=dev))
-        ms, kms, launches, clocks = time_fn(lambda: ops.topk(Q, X, metric, k), 1)
-        bytes_alg = N * D * 4
-        ach = bytes_alg / (kms * 1e-3) / 1e9
+        fl = ops.FLAG_NO_TENSOR if w in ("l2_fp32", "cos_fp32") else 0
+        ms, kern, launches, clocks, steps = time_fn(lambda: ops.topk(Q, X, metric, k, flags=fl), ((1, "scan"),))
+        kms = kern.get("scan", ms)
         cpu = None
         if not args.no_cpu:
             from oracle import search as OS
             ns = min(N, 100_000)
-            Xs, Qs = X[:ns].cpu().numpy(), Q.cpu().numpy()
+            Xs, Qs = X[:ns].cpu().numpy(), Q[:64].cpu().numpy()
             cpu = side_cpu_baseline("blas", "queries/s", lambda: OS.topk_search(Qs, Xs, metric, k, dtype=np.float32),
-                                    nq * ns / N, f"{nq} queries vs the first {ns} rows (NumPy port, scaled linearly to {N} rows)")
-        line = {"metric": f"queries/sec ({metric} top-{k}, {N}x{D} fp32 DB, {nq}-query batch)", "value": nq / (ms * 1e-3),
-                "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                                    len(Qs) * ns / N, f"{len(Qs)} queries vs the first {ns} rows (NumPy port, scaled linearly to {N} rows)")
+        roof = hbm_roofline("scan_topk", kms, N * D * 4)
+        if nq > 16:
+            # batch regime: more queries than one pass holds -> FP32-issue bound (2 lane-instructions per element pair)
+            lane_ops = 2.0 * nq * N * D
+            peak = 148 * 128 * 1.965e9
+            roof = {"bound": "fp32-alu", "kernel": "scan_topk", "achieved": lane_ops / (kms * 1e-3) / 1e12, "peak": peak / 1e12,
+                    "unit": "T lane-instr/s", "frac": lane_ops / (kms * 1e-3) / peak, "kernel_ms": kms, "traffic": None,
+                    "note": "batch regime (SURVEY 8d): 2 fp32 lane-instructions per element pair; peak = 148 SMs x 128 lanes x 1.965 GHz"}
+        return {"metric": f"queries/sec ({metric} top-{k}, {N}x{D} fp32 DB, {nq}-query batch)", "value": nq / (ms * 1e-3),
+                "unit": "queries/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                 "higher_is_better": True, "dtype": "f32", "data": "synthetic relu(N(0,1))",
                 "config": {"workload": f"{w}: {metric} top-{k}, {N}x{D} fp32, Q={nq}", "l2_policy": "inputs larger than L2"},
-                "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "scan_topk", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                             "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel_ms": kms,
-                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}, "cpu_baseline": cpu}
-        print(json.dumps(line))
-    elif w == "histogram":
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+    if w in ("cos_tensor_fp32", "l2_tensor_fp32"):
+        # fp32 store on the tcgen05 path: three-term bf16 split + exact fp32 re-rank + certificate (prepared index)
+        D, N, nq, k = args.dim or DIM, args.rows or ROWS_PER_GPU, args.queries or NQ, args.k or TOPK
+        metric = "cosine_similarity" if w == "cos_tensor_fp32" else "l2"
+        X = make_unit_rows(torch, N, D, 2101, dev, torch.float32)
+        Q = make_unit_rows(torch, nq, D, 2102, dev, torch.float32)
+        idx = ops.prepare_index(X)
+        ms, kern, launches, clocks, steps = time_fn(lambda: ops.topk(Q, idx, metric, k), KERNEL_TAGS)
+        fb = ops.last_fallback_count()
+        kms = kern.get("gemm_topk(tcgen05)", ms)
+        cpu = None
+        if not args.no_cpu:
+            cpu = cpu_torch_baseline(Q.cpu().numpy(), X.cpu().numpy(), k, budget_s=6.0)
+        roof = roofline_tensor(pk, "gemm_topk(tcgen05, 3-term bf16 split)", kms, 2.0 * nq * N * D, kern)
+        roof["tensor_flops_issued_per_launch"] = 3 * roof["algorithmic_flops_per_launch"]
+        roof["frac_of_issued_flops_burst"] = 3 * roof["frac_burst"]
+        return {"metric": f"queries/sec ({metric} top-{k}, {N}x{D} fp32 DB, {nq}-query batch)", "value": nq / (ms * 1e-3),
+                "unit": "queries/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                "higher_is_better": True, "dtype": "f32 (bf16 hi+lo split on tensor cores, exact fp32 re-rank)",
+                "data": "synthetic row-normalised N(0,1)", "fallback_queries_per_step": fb,
+                "config": {"workload": f"{w}: {metric} top-{k}, {N}x{D} fp32, Q={nq}", "l2_policy": "inputs larger than L2"},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+    if w == "histogram":
         B = args.rows or 8192
         g = torch.Generator(device=dev); g.manual_seed(1001)
         imgs = torch.randint(0, 256, (B, 224, 224, 3), generator=g, device=dev, dtype=torch.uint8)
         cs = "hsv" if args.hsv else "rgb"
-        ms, kms, launches, clocks = time_fn(lambda: ops.histogram(imgs, cs), 6)
-        bytes_alg = B * (224 * 224 * 3 + 512 * 4)
-        ach = bytes_alg / (kms * 1e-3) / 1e9
+        ms, kern, launches, clocks, steps = time_fn(lambda: ops.histogram(imgs, cs), ((6, "hist"),))
+        kms = kern.get("hist", ms)
         cpu = None
         if not args.no_cpu:
             from oracle import histogram as OH
             hs = imgs[:64].cpu().numpy()
             cpu = side_cpu_baseline("numpy", "images/s", lambda: OH.histogram(hs, cs), 64, f"64 images, NumPy bincount port ({cs})")
-        line = {"metric": f"images/sec (512-bin {cs} histogram, 224x224x3 uint8)", "value": B / (ms * 1e-3), "unit": "images/s",
-                "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        return {"metric": f"images/sec (512-bin {cs} histogram, 224x224x3 uint8)", "value": B / (ms * 1e-3), "unit": "images/s",
+                "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
                 "dtype": "u8", "data": "synthetic uniform pixels",
                 "config": {"workload": f"histogram {cs}: {B} images 224x224x3", "l2_policy": "inputs larger than L2"},
-                "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "histogram", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                             "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel_ms": kms,
-                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}, "cpu_baseline": cpu}
-        print(json.dumps(line))
-    elif w == "config5":
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": hbm_roofline("histogram", kms, B * (224 * 224 * 3 + 512 * 4)), "cpu_baseline": cpu}
+    if w == "config5":
         # BASELINE configs[4]: all-pairs evaluation (5 metrics, 4 relationship types, density histograms + PR counts)
         N = args.rows or 100_000
         D = args.dim or 512
@@ -492,7 +702,8 @@ def run_side(args):
         cat, col = (ids // 3).int(), (ids % 3).int()           # 10 categories x 3 colours (imageProcessing.py:60-62)
         ranges = {"cosine_distance": (0.0, 2.0), "l1_distance": (0.0, 2.0), "l2_distance": (0.0, 2.5),
                   "linf_distance": (0.0, 8.0), "magnitude_difference": (0.0, 6.0)}
-        ms, kms, launches, clocks = time_fn(lambda: ops.allpairs_eval(X, cat, col, ranges, 1024), 1)
+        ms, kern, launches, clocks, steps = time_fn(lambda: ops.allpairs_eval(X, cat, col, ranges, 1024), ((1, "scan"),))
+        kms = kern.get("scan", ms)
         pairs = N * (N - 1) / 2
         cpu = None
         if not args.no_cpu:
@@ -505,28 +716,28 @@ def run_side(args):
                                     ns * (ns - 1) / 2, f"all pairs of the first {ns} rows, vectorised NumPy port of the five metrics + binning")
         lane_ops = pairs * D * 5.25                              # dot, |d|, d^2, max|d| + shared x^2: instructions per element pair
         peak = 148 * 128 * 1.965e9
-        line = {"metric": f"pairs/sec (all-pairs evaluation, {N}x{N}, D={D}, 5 metrics)", "value": pairs / (ms * 1e-3), "unit": "pairs/s",
-                "n_gpus": 1, "steps": args.steps, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic N(0,1)",
+        return {"metric": f"pairs/sec (all-pairs evaluation, {N}x{N}, D={D}, 5 metrics)", "value": pairs / (ms * 1e-3), "unit": "pairs/s",
+                "n_gpus": 1, "steps": steps, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic N(0,1)",
                 "config": {"workload": "configs[4]: all-pairs distance-density + precision-recall counts, five metrics"},
-                "gpu_launches": int(launches), "clocks": clocks,
+                "gpu_launches": launches, "clocks": clocks,
                 "roofline": {"bound": "fp32-alu", "kernel": "scan_topk<K_EVAL>", "achieved": lane_ops / (kms * 1e-3) / 1e12,
                              "peak": peak / 1e12, "unit": "T lane-instr/s", "frac": lane_ops / (kms * 1e-3) / peak, "kernel_ms": kms,
+                             "traffic": None,
                              "note": "CUDA-core bound: 5.25 fp32 lane-instructions per element pair; peak = 148 SMs x 128 lanes x 1.965 GHz"},
                 "cpu_baseline": cpu}
-        print(json.dumps(line))
-    elif w == "resize":
+    if w == "resize":
         # image front-end: PIL-exact bicubic resize (shorter edge -> 224) + centre crop, then the 512-bin histogram
         B = args.rows or 2048
         H, W = 480, 640
         g = torch.Generator(device=dev); g.manual_seed(1003)
         imgs = torch.randint(0, 256, (B, H, W, 3), generator=g, device=dev, dtype=torch.uint8)
-        ms, kms, launches, clocks = time_fn(lambda: ops.histogram(ops.resize_crop(imgs, 224)), 8)
+        ms, kern, launches, clocks, steps = time_fn(lambda: ops.histogram(ops.resize_crop(imgs, 224)), ((8, "resize"),))
+        kms = kern.get("resize", ms)
         rh, rw = ops.shortest_edge_size(H, W, 224)
         scale = W / rw
         left = (rw - 224) // 2
         cols = min(W, int((left + 224) * scale + 2 * scale + 1)) - max(0, int(left * scale - 2 * scale))
         bytes_alg = B * (H * cols * 3 + 224 * 224 * 3)            # source window the crop depends on + cropped output
-        ach = bytes_alg / (kms * 1e-3) / 1e9
         cpu = None
         if not args.no_cpu:
             try:
@@ -544,16 +755,12 @@ def run_side(args):
                                         "processor front-end) + NumPy histogram, one core")
             except ImportError:
                 cpu = None
-        line = {"metric": f"images/sec (bicubic resize {H}x{W} -> 224 crop + 512-bin histogram)", "value": B / (ms * 1e-3),
-                "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        return {"metric": f"images/sec (bicubic resize {H}x{W} -> 224 crop + 512-bin histogram)", "value": B / (ms * 1e-3),
+                "unit": "images/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                 "higher_is_better": True, "dtype": "u8", "data": "synthetic uniform pixels",
                 "config": {"workload": f"resize: {B} images {H}x{W}x3 -> 224x224x3 -> histogram", "l2_policy": "inputs larger than L2"},
-                "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "resize_crop", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                             "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel_ms": kms,
-                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}, "cpu_baseline": cpu}
-        print(json.dumps(line))
-    elif w == "pairs":
+                "gpu_launches": launches, "clocks": clocks, "roofline": hbm_roofline("resize_crop", kms, bytes_alg), "cpu_baseline": cpu}
+    if w == "pairs":
         # explicit pair lists (mi_analysis.py:256-297): P random pairs over an N x D fp32 store, seven values per pair
         N = args.rows or 1_000_000
         D = args.dim or 512
@@ -562,9 +769,8 @@ def run_side(args):
         X = torch.randn((N, D), generator=g, device=dev)
         ia = torch.randint(0, N, (P,), generator=g, device=dev)
         ib = torch.randint(0, N, (P,), generator=g, device=dev)
-        ms, kms, launches, clocks = time_fn(lambda: ops.pair_metrics(X, None, ia, ib), 7)
-        bytes_alg = P * (2 * D * 4 + 16 + 28)
-        ach = bytes_alg / (kms * 1e-3) / 1e9
+        ms, kern, launches, clocks, steps = time_fn(lambda: ops.pair_metrics(X, None, ia, ib), ((7, "pairs"),))
+        kms = kern.get("pairs", ms)
         cpu = None
         if not args.no_cpu:
             from oracle import metrics as OM
@@ -572,16 +778,13 @@ def run_side(args):
             Xa, Xb = X[ia[:ns]].cpu().numpy(), X[ib[:ns]].cpu().numpy()
             cpu = side_cpu_baseline("loop", "pairs/s", lambda: [OM.get_all_metrics(a, b) for a, b in zip(Xa, Xb)], ns,
                                     f"{ns} pairs, get_all_metrics per pair (the reference loop mi_analysis.py:277-291), one core")
-        line = {"metric": f"pairs/sec (get_all_metrics over an explicit pair list, {N}x{D} fp32 store)", "value": P / (ms * 1e-3),
-                "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        return {"metric": f"pairs/sec (get_all_metrics over an explicit pair list, {N}x{D} fp32 store)", "value": P / (ms * 1e-3),
+                "unit": "pairs/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                 "higher_is_better": True, "dtype": "f32", "data": "synthetic N(0,1), uniform random pairs",
                 "config": {"workload": f"pairs: {P} pairs over {N}x{D} fp32", "l2_policy": "inputs larger than L2"},
-                "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "pair_metrics", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                             "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel_ms": kms,
-                             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["_source"]}, "cpu_baseline": cpu}
-        print(json.dumps(line))
-    elif w == "config1":
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": hbm_roofline("pair_metrics", kms, P * (2 * D * 4 + 16 + 28)), "cpu_baseline": cpu}
+    if w == "config1":
         def palette_images(b, seed):
             """a few flat colour blocks + small noise per image: peaky histograms with many exact ties"""
             g = torch.Generator(device=dev); g.manual_seed(seed)
@@ -596,7 +799,8 @@ def run_side(args):
             X = ops.counts_to_embedding(ops.histogram(di))[0]
             Qm = ops.counts_to_embedding(ops.histogram(qi))[0]
             return ops.topk(Qm, X, "l2", 10)
-        ms, kms, launches, clocks = time_fn(fn, 1)
+        ms, kern, launches, clocks, steps = time_fn(fn, KERNEL_TAGS + ((6, "histogram"),))
+        fb = ops.last_fallback_count()
         cpu = None
         if not args.no_cpu:
             from oracle import histogram as OH
@@ -609,72 +813,27 @@ def run_side(args):
                 return OS.topk_search(Qc, Xc, "l2", 10, dtype=np.float32)
             cpu = side_cpu_baseline("numpy", "queries/s", cpu_pass, 100, "100 query + 1000 database images (a tenth of config 1 on "
                                     "both sides, same 10 database images per query: histogram port + NumPy L2 top-10)")
-        line = {"metric": "queries/sec (config 1: histogram embeddings of 1k+10k images, L2 top-10 over 10kx512 fp32)",
-                "value": 1000 / (ms * 1e-3), "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": ms,
+        return {"metric": "queries/sec (config 1: histogram embeddings of 1k+10k images, L2 top-10 over 10kx512 fp32)",
+                "value": 1000 / (ms * 1e-3), "unit": "queries/s", "n_gpus": 1, "steps": steps, "ms_per_step": ms,
                 "higher_is_better": True, "dtype": "u8 -> f32", "data": "synthetic palette images",
-                "config": {"workload": "configs[0]"}, "gpu_launches": int(launches), "clocks": clocks, "scan_kernel_ms": kms,
-                "cpu_baseline": cpu}
-        print(json.dumps(line))
-    else:
-        raise SystemExit(f"unknown workload {w}")
-    return 0
+                "config": {"workload": "configs[0]"}, "gpu_launches": launches, "clocks": clocks, "kernels_ms": kern,
+                "fallback_queries_per_step": fb, "cpu_baseline": cpu}
+    raise SystemExit(f"unknown workload {w}")
 
 
 def run_config4(args):
-    """BASELINE configs[3]: 10M x 512 database row-sharded over the ranks (strong scaling: total rows fixed), all five
-    metrics, one all-gather + merge per search.  bf16 rows for the tensor-core metrics (10k queries, k=100), fp32 rows
-    for L1 / Linf (8 queries, k=10).  Prints one JSON line with per-metric queries/s (max over ranks)."""
+    """BASELINE configs[3] on its own: python bench.py --workload config4 [--strong-rows N] (torchrun for N > 1)."""
     import torch
     import torch.distributed as dist
-    from image_retrieval_b200 import ops
-    from image_retrieval_b200.sharded import ShardedIndex, shard_range
     rank, world, local = dist_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         init_nccl(torch, dist, dev)
-    total = args.rows or 10_000_000
-    b, e = shard_range(total, world, rank)
-    n_local = e - b
-    res = {}
-
-    def timed(fn):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
-
-    Xb = make_unit_rows(torch, n_local, DIM, 4001 + rank, dev, torch.bfloat16)
-    Qb = make_unit_rows(torch, NQ, DIM, 4002, dev, torch.bfloat16)
-    idx = ShardedIndex(Xb, b)
-    for metric in ("cosine_similarity", "angular_distance", "l2"):
-        ms = timed(lambda: idx.topk(Qb, metric, TOPK))
-        res[metric] = {"queries": NQ, "k": TOPK, "dtype": "bf16", "ms": ms, "queries_per_s": NQ / (ms * 1e-3)}
-    del Xb, idx
-    torch.cuda.empty_cache()
-    Xf = make_unit_rows(torch, n_local, DIM, 4001 + rank, dev, torch.float32)
-    Qf = make_unit_rows(torch, 8, DIM, 4003, dev, torch.float32)
-    idx = ShardedIndex(Xf, b)
-    for metric in ("l1", "linf"):
-        ms = timed(lambda: idx.topk(Qf, metric, 10))
-        res[metric] = {"queries": 8, "k": 10, "dtype": "f32", "ms": ms, "queries_per_s": 8 / (ms * 1e-3),
-                       "hbm_GBps_per_gpu": n_local * DIM * 4 / (ms * 1e-3) / 1e9}
+    res = strong_config4(args, torch, dist, world, rank, local, dev)
     if rank == 0:
         print(json.dumps({"metric": "queries/sec per metric (config 4: 10M x 512 row-sharded, all-gather top-k merge)",
-                          "n_gpus": world, "steps": args.steps, "db_rows_total": total, "rows_per_gpu": n_local,
-                          "scaling": "strong", "results": res}))
+                          "n_gpus": world, **res}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -689,7 +848,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline")
     ap.add_argument("--no-tensor", action="store_true", help="force the CUDA-core scan path")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the oracle parity check")
+    ap.add_argument("--no-side", action="store_true", help="headline: skip the side rows")
+    ap.add_argument("--no-strong", action="store_true", help="headline: skip the config-4 strong-scaling sub-record")
+    ap.add_argument("--strong-rows", type=int, default=10_000_000)
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--dim", type=int, default=0)
     ap.add_argument("--queries", type=int, default=0)

@@ -33,9 +33,10 @@ def _round_up(a, b):
 
 
 class ShardedIndex:
-    def __init__(self, local_rows, row_begin, group=None, local_topk=None, merge=None):
-        # default (CUDA) path: keep the per-shard search state (row norms, split planes) next to the rows
-        if local_topk is None and isinstance(local_rows, torch.Tensor) and local_rows.is_cuda:
+    def __init__(self, local_rows, row_begin, group=None, local_topk=None, merge=None, prepare=True):
+        # default (CUDA) path: keep the per-shard search state (row norms, split planes) next to the rows;
+        # prepare=False skips it (stores that are only searched with L1 / Linf / optimized have no use for it)
+        if prepare and local_topk is None and isinstance(local_rows, torch.Tensor) and local_rows.is_cuda:
             local_rows = ops.prepare_index(local_rows)
         self.X = local_rows
         self.row_begin = int(row_begin)
