@@ -10,7 +10,9 @@ L1, L2, LINF, COS_SIM, COS_DIST, ANGLE, MAG_DIFF, OPTIMIZED = range(8)
 F32, BF16 = 0, 1
 FLAG_RAW, FLAG_ABS_SCORE, FLAG_NO_TENSOR, FLAG_NO_RERANK, FLAG_HAVE_INDEX = 1, 2, 4, 8, 16
 RGB, HSV = 0, 1
-MAX_K = 256
+MAX_K = 256          # one result page
+MAX_K_PAGED = 4096    # longest list ops.topk serves through b200ir_topk_paged + b200ir_sort_topk_rows
+MAX_CANDIDATES = 1024 # longest candidate list of b200ir_rank_candidates
 
 c_i64 = ctypes.c_int64
 c_vp = ctypes.c_void_p
@@ -32,6 +34,17 @@ _SIGNATURES = {
     "b200ir_topk_indexed": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp, c_i64, c_vp, c_i64, ctypes.c_int, ctypes.c_int,
                                            c_i64, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_vp, c_vp, c_vp, ctypes.c_size_t,
                                            c_vp, ctypes.c_size_t, c_vp]),
+    "b200ir_topk_paged": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp, c_i64, c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_i64,
+                                         ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "b200ir_sort_topk_rows": (ctypes.c_int, [ctypes.c_int, c_vp, c_vp, c_i64, ctypes.c_int, c_vp]),
+    "b200ir_topk_multi_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int, c_i64, c_i64,
+                                                            ctypes.c_int, ctypes.c_int]),
+    "b200ir_topk_multi": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int, c_vp, c_i64, c_vp, c_i64, ctypes.c_int,
+                                         ctypes.c_int, c_i64, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_vp, c_vp, c_vp,
+                                         ctypes.c_size_t, c_vp]),
+    "b200ir_candidate_metrics": (ctypes.c_int, [ctypes.c_int, c_vp, c_i64, c_vp, c_i64, ctypes.c_int, c_vp, ctypes.c_int, c_vp, c_vp]),
+    "b200ir_rank_candidates": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_int, c_vp, c_vp,
+                                              c_vp, c_vp, c_vp]),
     "b200ir_pairwise_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, c_i64, c_i64, ctypes.c_int]),
     "b200ir_pairwise": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp, c_i64, c_vp, c_i64, ctypes.c_int,
                                        ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_vp, c_vp, ctypes.c_size_t, c_vp]),

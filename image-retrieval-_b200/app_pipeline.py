@@ -54,6 +54,14 @@ class _TrackedDict(dict):
     def setdefault(self, k, d=None):
         r = super().setdefault(k, d); self._bump(); return r
 
+    def __ior__(self, other):
+        super().update(other); self._bump(); return self
+
+    def invalidate(self):
+        """Call after editing a stored row IN PLACE (e.g. app.embeddings[p][:] = v): the device copy of the store is
+        rebuilt on the next search.  Assignments, deletions, update() and |= are tracked automatically."""
+        self._bump()
+
 
 class EnhancedImageSearchApp:
     """Enhanced image search application with geometric metrics."""
@@ -200,7 +208,9 @@ class EnhancedImageSearchApp:
         q = self._get_query_embedding(query)
         if top_k <= 0:
             return []
-        k = min(int(top_k), len(paths), ops.MAX_K)
+        k = min(int(top_k), len(paths))               # results[:top_k] for any top_k (:172); lists beyond one page are paged
+        if k > ops.MAX_K_PAGED:
+            raise ValueError(f"search_images: top_k up to {ops.MAX_K_PAGED} rows is supported, got {top_k}")
         if use_optimized_similarity:
             s, i = ops.topk(q, X, "optimized_similarity", k, abs_score=True, params=self.searcher.similarity_params)
         else:
@@ -214,13 +224,22 @@ class EnhancedImageSearchApp:
             return {'analysis': {'intersections': {}, 'unique_contributions': {}}}
         paths, X = self._store()
         q = self._get_query_embedding(query)
-        k = max(1, min(int(top_k), len(paths), ops.MAX_K))
+        k = max(1, min(int(top_k), len(paths)))
+        names = (('cosine_similarity', 1.0), ('l1_distance', -1.0), ('l2_distance', -1.0))
+        if k <= ops.MAX_K:
+            # the reference's three scans + three sorts (:296-328) as ONE pass that keeps three candidate lists
+            S, I = ops.topk_multi(q, X, [n for n, _ in names], k)
+            S, I = S[:, 0].cpu().numpy(), I[:, 0].cpu().numpy()
+        else:
+            if k > ops.MAX_K_PAGED:
+                raise ValueError(f"search_with_multiple_metrics: top_k up to {ops.MAX_K_PAGED} rows is supported, got {top_k}")
+            pages = [ops.topk(q, X, n, k) for n, _ in names]
+            S = np.stack([p[0][0].cpu().numpy() for p in pages])
+            I = np.stack([p[1][0].cpu().numpy() for p in pages])
         results_by_metric = {}
-        for name, sign in (('cosine_similarity', 1.0), ('l1_distance', -1.0), ('l2_distance', -1.0)):
-            s, i = ops.topk(q, X, name, k)
-            s, i = s[0].cpu().numpy(), i[0].cpu().numpy()
+        for y, (name, sign) in enumerate(names):
             results_by_metric[name] = [{'path': paths[j], name: v, 'score': sign * v}
-                                       for v, j in zip(s, i) if j >= 0][:max(0, int(top_k))]
+                                       for v, j in zip(S[y], I[y]) if j >= 0][:max(0, int(top_k))]
         results_by_metric['analysis'] = _overlap_analysis(results_by_metric, top_k)
         return results_by_metric
 

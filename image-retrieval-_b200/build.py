@@ -18,7 +18,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
-KINDS = ["K_L1", "K_L2", "K_LINF", "K_DOT", "K_MULTI"]
+KINDS = ["K_L1", "K_L2", "K_LINF", "K_DOT", "K_MULTI", "K_MULTI6"]
 
 
 def units():

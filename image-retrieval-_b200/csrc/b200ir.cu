@@ -7,6 +7,7 @@
 #include "pairs.cuh"
 #include "resize.cuh"
 #include "postfilter.cuh"
+#include "rank.cuh"
 #include "gemm_topk.h"
 #include "profile.h"
 
@@ -245,6 +246,131 @@ static int topk_impl(int metric, int dtype, const void* Q, int64_t nq, const voi
 }
 
 extern "C" {
+
+int b200ir_topk_paged(int metric, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D, int k,
+                      int64_t index_offset, int flags, const float* weights_host, const uint64_t* after, uint64_t* last,
+                      float* out_score, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!valid_metric(metric) || !valid_dtype(dtype) || nq < 0 || N <= 0 || D <= 0) return B200IR_E_ARG;
+  if (k < 1 || k > B200IR_MAX_K) return B200IR_E_K;
+  if (N >= (int64_t(1) << 32)) return B200IR_E_SHAPE;
+  if (nq == 0) return 0;
+  if (!Q || !X || !out_score || !out_idx) return B200IR_E_ARG;
+  if (reinterpret_cast<uintptr_t>(Q) % elem_size(dtype) || reinterpret_cast<uintptr_t>(X) % elem_size(dtype)) return B200IR_E_ALIGN;
+  const ScanPlan pl = make_scan_plan(metric, dtype, nq, N, D, k, false);
+  if (!workspace || workspace_bytes < pl.total_bytes) return B200IR_E_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return B200IR_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const MetricParams mp = make_params(metric, flags, D, weights_host);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  cudaError_t e = run_scan(pl, dtype, Q, nq, X, N, D, k, mp, ws, nullptr, st, after, 0);
+  if (e != cudaSuccess) return int(e);
+  FinalizeOpts fo;
+  fo.last_key = last;
+  return int(launch_finalize(reinterpret_cast<const uint64_t*>(ws + pl.off_partial), nq, int64_t(pl.P) * k, k, mp, index_offset,
+                             out_score, out_idx, st, fo));
+}
+
+int b200ir_sort_topk_rows(int descending, float* score, int64_t* idx, int64_t nq, int K, void* stream) {
+  if (nq < 0 || K < 1 || K > kSortRowsMax || nq > 0x7fffffff) return B200IR_E_ARG;
+  if (nq == 0) return 0;
+  if (!score || !idx) return B200IR_E_ARG;
+  int n = 1;
+  while (n < K) n <<= 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = size_t(n) * sizeof(key128_t);
+  cudaError_t e = cudaFuncSetAttribute(sort_topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSortRowsMax * sizeof(key128_t)));
+  if (e != cudaSuccess) return int(e);
+  ProfileScope ps(PT_MERGE, st);
+  sort_topk_rows_kernel<<<unsigned(nq), 256, smem, st>>>(descending ? 1 : 0, score, idx, K, n);
+  return int(cudaGetLastError());
+}
+
+static int multi_kind_mask(const int* metrics_host, int nmetrics) {
+  if (!metrics_host || nmetrics < 1 || nmetrics > B200IR_NUM_METRICS) return -1;
+  int mask = 0;
+  for (int i = 0; i < nmetrics; ++i) {
+    if (!valid_metric(metrics_host[i])) return -1;
+    mask |= 1 << rank_kind_of(metrics_host[i]);
+  }
+  return mask;
+}
+
+size_t b200ir_topk_multi_workspace_bytes(const int* metrics_host, int nmetrics, int dtype, int64_t nq, int64_t N, int D, int k) {
+  const int mask = multi_kind_mask(metrics_host, nmetrics);
+  if (mask <= 0 || !valid_dtype(dtype) || nq <= 0 || N <= 0 || D <= 0 || k < 1 || k > B200IR_MAX_K) return 0;
+  return make_scan_plan(B200IR_OPTIMIZED, dtype, nq, N, D, k, false, __builtin_popcount(mask)).total_bytes;
+}
+
+int b200ir_topk_multi(const int* metrics_host, int nmetrics, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D,
+                      int k, int64_t index_offset, int flags, const float* weights_host, float* out_score, int64_t* out_idx,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  const int mask = multi_kind_mask(metrics_host, nmetrics);
+  if (mask <= 0 || !valid_dtype(dtype) || nq < 0 || N < 0 || D <= 0) return B200IR_E_ARG;
+  if (k < 1 || k > B200IR_MAX_K) return B200IR_E_K;
+  if (N >= (int64_t(1) << 32)) return B200IR_E_SHAPE;
+  if (nq == 0) return 0;
+  if (!Q || !out_score || !out_idx || (N > 0 && !X)) return B200IR_E_ARG;
+  if (reinterpret_cast<uintptr_t>(Q) % elem_size(dtype) || reinterpret_cast<uintptr_t>(X) % elem_size(dtype)) return B200IR_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N == 0) {
+    ProfileScope ps(PT_MISC, st);
+    for (int y = 0; y < nmetrics; ++y) {
+      const int64_t n = nq * k;
+      fill_empty_topk_kernel<<<int(ceil_div64(n, 256)), 256, 0, st>>>(out_score + y * n, out_idx + y * n, n,
+                                                                     metric_descending(metrics_host[y]) ? -INFINITY : INFINITY);
+    }
+    return int(cudaGetLastError());
+  }
+  const int nl = __builtin_popcount(mask);
+  const ScanPlan pl = make_scan_plan(B200IR_OPTIMIZED, dtype, nq, N, D, k, false, nl);
+  if (!workspace || workspace_bytes < pl.total_bytes) return B200IR_E_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return B200IR_E_ALIGN;
+  // weights feed the optimized ranking (geometric_metrics.py:78-82 defaults when NULL)
+  MetricParams mp = make_params(B200IR_OPTIMIZED, flags, D, weights_host);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  cudaError_t e = run_scan(pl, dtype, Q, nq, X, N, D, k, mp, ws, nullptr, st, nullptr, mask);
+  if (e != cudaSuccess) return int(e);
+  FinalizeOpts fo;
+  fo.nmetrics = nmetrics;
+  int slot_of_kind[RK_COUNT], next = 0;
+  for (int m = 0; m < RK_COUNT; ++m) slot_of_kind[m] = (mask >> m) & 1 ? next++ : -1;
+  for (int y = 0; y < nmetrics; ++y) {
+    fo.slot[y] = (signed char)slot_of_kind[rank_kind_of(metrics_host[y])];
+    fo.metric[y] = (signed char)metrics_host[y];
+  }
+  fo.list_stride = nq * int64_t(pl.P) * k;
+  fo.out_stride = nq * int64_t(k);
+  return int(launch_finalize(reinterpret_cast<const uint64_t*>(ws + pl.off_partial), nq, int64_t(pl.P) * k, k, mp, index_offset,
+                             out_score, out_idx, st, fo));
+}
+
+int b200ir_candidate_metrics(int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D, const int64_t* cand_idx, int kc,
+                             float* out, void* stream) {
+  if (!valid_dtype(dtype) || nq < 0 || N < 0 || D <= 0 || kc < 1) return B200IR_E_ARG;
+  if (nq == 0) return 0;
+  if (!Q || !cand_idx || !out || (N > 0 && !X)) return B200IR_E_ARG;
+  if (reinterpret_cast<uintptr_t>(Q) % elem_size(dtype) || reinterpret_cast<uintptr_t>(X) % elem_size(dtype)) return B200IR_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope ps(PT_MISC, st);
+  if (dtype == B200IR_F32) return int(launch_pair_metrics<float>(Q, nq, X, N, D, nullptr, cand_idx, nq * kc, out, st, kc));
+  return int(launch_pair_metrics<__nv_bfloat16>(Q, nq, X, N, D, nullptr, cand_idx, nq * kc, out, st, kc));
+}
+
+int b200ir_rank_candidates(const float* pair_vals, const int64_t* cand_idx, int64_t nq, int kc, const float* weights_host, int k,
+                           float* out_optimized, int32_t* out_pos, float* out_val, int64_t* out_row, void* stream) {
+  if (nq < 0 || kc < 1 || kc > kRankMaxCand || k < 1 || k > kc || nq > 0x7fffffff) return B200IR_E_ARG;
+  if (nq == 0) return 0;
+  if (!pair_vals || !cand_idx || !out_pos || !out_val || !out_row) return B200IR_E_ARG;
+  float w[5] = {1.f, 0.f, 0.f, 0.f, 0.f};                       // geometric_metrics.py:78-82
+  if (weights_host) for (int i = 0; i < 5; ++i) w[i] = weights_host[i];
+  int n = 1;
+  while (n < kc) n <<= 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfileScope ps(PT_MISC, st);
+  rank_candidates_kernel<<<unsigned(nq), 128, 0, st>>>(pair_vals, cand_idx, nq, kc, n, w[0], w[1], w[2], w[3], w[4], k, out_optimized,
+                                                      out_pos, out_val, out_row);
+  return int(cudaGetLastError());
+}
 
 size_t b200ir_pairwise_workspace_bytes(int metric, int dtype, int64_t nq, int64_t N, int D) {
   if (!valid_metric(metric) || !valid_dtype(dtype) || nq <= 0 || N <= 0 || D <= 0) return 0;

@@ -48,12 +48,12 @@ template <> struct PairVec<__nv_bfloat16> {
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) pair_metrics_kernel(const T* __restrict__ A, int64_t NA, const T* __restrict__ B,
                                                            int64_t NB, int D, const int64_t* __restrict__ ia,
-                                                           const int64_t* __restrict__ ib, int64_t P,
+                                                           const int64_t* __restrict__ ib, int64_t P, int ia_group,
                                                            float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   for (int64_t p = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; p < P; p += warps) {
-    const int64_t i = ia[p], j = ib[p];
+    const int64_t i = ia != nullptr ? ia[p] : p / ia_group, j = ib[p];     // ia == nullptr: candidate lists, ia_group per row of A
     if (i < 0 || i >= NA || j < 0 || j >= NB) {      // unknown row: the pair is reported as NaN, never read
       if (lane < kPairOutputs) out[int64_t(lane) * P + p] = __int_as_float(0x7fc00000);
       continue;
@@ -95,12 +95,12 @@ __global__ void __launch_bounds__(256) pair_metrics_kernel(const T* __restrict__
 
 template <typename T>
 inline cudaError_t launch_pair_metrics(const void* A, int64_t NA, const void* B, int64_t NB, int D, const int64_t* ia,
-                                       const int64_t* ib, int64_t P, float* out, cudaStream_t st) {
+                                       const int64_t* ib, int64_t P, float* out, cudaStream_t st, int ia_group = 1) {
   const int64_t want = ceil_div64(P, 8);
   const int blocks = int(want < int64_t(kNumSMs) * 8 * 4 ? want : int64_t(kNumSMs) * 8 * 4);   // grid-stride past 8 CTAs/SM x 4 waves
   const bool vec = D % PairVec<T>::kElems == 0 && reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0;
-  if (vec) pair_metrics_kernel<T, true><<<blocks, 256, 0, st>>>(static_cast<const T*>(A), NA, static_cast<const T*>(B), NB, D, ia, ib, P, out);
-  else pair_metrics_kernel<T, false><<<blocks, 256, 0, st>>>(static_cast<const T*>(A), NA, static_cast<const T*>(B), NB, D, ia, ib, P, out);
+  if (vec) pair_metrics_kernel<T, true><<<blocks, 256, 0, st>>>(static_cast<const T*>(A), NA, static_cast<const T*>(B), NB, D, ia, ib, P, ia_group, out);
+  else pair_metrics_kernel<T, false><<<blocks, 256, 0, st>>>(static_cast<const T*>(A), NA, static_cast<const T*>(B), NB, D, ia, ib, P, ia_group, out);
   return cudaGetLastError();
 }
 

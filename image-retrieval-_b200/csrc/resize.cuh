@@ -271,12 +271,9 @@ __global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs 
 
 template <int KREG>
 inline cudaError_t launch_resize_crop(const ResizeArgs& a, int groups, int nb, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(resize_crop_kernel<KREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kResizeSmemBudget);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  // per launch: the attribute belongs to the current device / context (a process may use several GPUs) and is cheap to set
+  cudaError_t e = cudaFuncSetAttribute(resize_crop_kernel<KREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kResizeSmemBudget);
+  if (e != cudaSuccess) return e;
   resize_crop_kernel<KREG><<<dim3(groups, nb), kResizeThreads, smem, st>>>(a);
   return cudaGetLastError();
 }

@@ -5,7 +5,21 @@
 
 namespace b200ir {
 
-enum ScanKind { K_L1 = 0, K_L2 = 1, K_LINF = 2, K_DOT = 3, K_MULTI = 4, K_EVAL = 5 };
+enum ScanKind { K_L1 = 0, K_L2 = 1, K_LINF = 2, K_DOT = 3, K_MULTI = 4, K_EVAL = 5, K_MULTI6 = 6 };
+
+// K_MULTI6: ONE pass keeps up to six candidate lists per query, one per ranking (search_with_multiple_metrics,
+// app_pipeline.py:296-328 / image_search.py:199-219, runs one scan + sort per metric instead)
+enum RankKind { RK_COS = 0, RK_L1 = 1, RK_L2 = 2, RK_LINF = 3, RK_MAG = 4, RK_OPT = 5, RK_COUNT = 6 };
+__host__ __device__ inline int rank_kind_of(int metric) {
+  switch (metric) {
+    case B200IR_L1: return RK_L1;
+    case B200IR_L2: return RK_L2;
+    case B200IR_LINF: return RK_LINF;
+    case B200IR_MAG_DIFF: return RK_MAG;
+    case B200IR_OPTIMIZED: return RK_OPT;
+    default: return RK_COS;   // cosine similarity / distance / angle share the descending-cosine ranking
+  }
+}
 
 constexpr int kScanThreads = 128;   // == rows per tile (one row per thread)
 constexpr int kScanStages = 2;
@@ -45,6 +59,11 @@ struct ScanArgs {
   // [gate_base, gate_base + nq) of a device-side list whose length *gate is only known on the device
   const int* gate;        // nullptr: plain launch
   int gate_base;
+  // paging (result pages beyond B200IR_MAX_K): only keys strictly after the cursor of the previous page are candidates
+  const uint64_t* after;  // [nq] or nullptr
+  // K_MULTI6: list slot of each ranking kind (-1: not requested) and the number of lists kept per query
+  signed char lslot[RK_COUNT];
+  int nl;
   // all-pairs evaluation mode (K_EVAL): queries == database rows, pairs i < j only
   const int32_t* cat;     // [N] object category of each row
   const int32_t* col;     // [N] colour of each row
@@ -79,19 +98,21 @@ struct ScanPlan {
 
 inline int scan_sortn(int k) { return k <= 128 ? 256 : 512; }
 
-inline ScanPlan make_scan_plan(int metric, int dtype, int64_t nq, int64_t N, int D, int k, bool pairwise) {
+// nl > 1: multi-list scan (K_MULTI6) keeping nl candidate lists per query
+inline ScanPlan make_scan_plan(int metric, int dtype, int64_t nq, int64_t N, int D, int k, bool pairwise, int nl = 1) {
   ScanPlan pl{};
   const int kind = scan_kind_of(metric);
   const int esz = dtype == B200IR_F32 ? 4 : 2;
   const int DKE = kRowChunkBytes / esz;
-  const int tq_max = 8;
+  int tq_max = 8;
+  if (nl > 1 && nl * scan_sortn(k) * 8 * 8 > 100 * 1024) tq_max = 4;     // keep the lists of a CTA under ~100 KB
   (void)kind;
   pl.TQ = nq <= 1 ? 1 : (nq <= 4 ? 4 : tq_max);
   pl.G = int(ceil_div64(nq, pl.TQ));
   pl.nq_pad = pl.G * pl.TQ;
   pl.D_pad = int(round_up64(D, DKE));
   pl.sortn = pairwise ? 256 : scan_sortn(k);
-  pl.smem = size_t(kScanStages) * scan_stage_bytes(pl.TQ, DKE) + size_t(pl.TQ) * pl.sortn * 8 + pl.TQ * 16 + 64;
+  pl.smem = size_t(kScanStages) * scan_stage_bytes(pl.TQ, DKE) + size_t(pl.TQ) * nl * pl.sortn * 8 + pl.TQ * nl * 16 + 64;
   int ctas_per_sm = int((227 * 1024) / (pl.smem + 1024));      // 1 KB per resident CTA is reserved by the driver
   ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
   const int64_t target = int64_t(kNumSMs) * ctas_per_sm;
@@ -108,7 +129,7 @@ inline ScanPlan make_scan_plan(int metric, int dtype, int64_t nq, int64_t N, int
   pl.off_qf = off; off += round_up64(size_t(pl.nq_pad) * pl.D_pad * 4, 256);
   pl.off_qn = off; off += round_up64(size_t(pl.nq_pad) * 4, 256);
   pl.off_partial = off;
-  if (!pairwise) off += round_up64(size_t(nq) * pl.P * k * 8, 256);
+  if (!pairwise) off += round_up64(size_t(nl) * nq * pl.P * k * 8, 256);     // [nl][nq][P][k]
   pl.total_bytes = off;
   return pl;
 }
@@ -118,6 +139,7 @@ inline ScanPlan make_scan_plan(int metric, int dtype, int64_t nq, int64_t N, int
   cudaError_t launch_scan_##kind##_f32(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, int TQ, size_t smem, cudaStream_t st); \
   cudaError_t launch_scan_##kind##_bf16(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, int TQ, size_t smem, cudaStream_t st);
 B200IR_DECL_SCAN(K_L1) B200IR_DECL_SCAN(K_L2) B200IR_DECL_SCAN(K_LINF) B200IR_DECL_SCAN(K_DOT) B200IR_DECL_SCAN(K_MULTI)
+B200IR_DECL_SCAN(K_MULTI6)
 #undef B200IR_DECL_SCAN
 
 // Exact re-do of the queries a tensor-core search could not certify (gemm_topk.cu).  Their number is only known on the
@@ -138,9 +160,11 @@ cudaError_t run_fallback(const FallbackPlan& fp, int dtype, const void* Q, int64
 cudaError_t launch_prep_queries(int dtype, const void* Q, int nq, int D, int nq_pad, int D_pad, float* Qf, float* qn,
                                 cudaStream_t st);
 
-// Runs prep + scan.  In top-k mode leaves [nq, P, k] sorted keys at ws + plan.off_partial.
+// Runs prep + scan.  In top-k mode leaves [nq, P, k] sorted keys at ws + plan.off_partial.  `after`: paging cursor
+// per query (or nullptr).  kind_mask != 0: multi-list scan, [nl][nq][P][k] keys, list l = l-th set bit of kind_mask.
 cudaError_t run_scan(const ScanPlan& pl, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D, int k,
-                     const MetricParams& mp, unsigned char* ws, float* out_all, cudaStream_t st);
+                     const MetricParams& mp, unsigned char* ws, float* out_all, cudaStream_t st,
+                     const uint64_t* after = nullptr, int kind_mask = 0);
 
 size_t allpairs_eval_workspace_bytes(int64_t N, int D, int nthr);
 cudaError_t run_allpairs_eval(const float* X, const int32_t* cat, const int32_t* col, int64_t N, int D, int nbins,

@@ -44,12 +44,13 @@ static cudaError_t dispatch_scan(int kind, bool f32, const CUtensorMap& tmX, con
     case K_LINF:  return f32 ? launch_scan_K_LINF_f32(tmX, tmQ, a, TQ, smem, st)  : launch_scan_K_LINF_bf16(tmX, tmQ, a, TQ, smem, st);
     case K_DOT:   return f32 ? launch_scan_K_DOT_f32(tmX, tmQ, a, TQ, smem, st)   : launch_scan_K_DOT_bf16(tmX, tmQ, a, TQ, smem, st);
     case K_MULTI: return f32 ? launch_scan_K_MULTI_f32(tmX, tmQ, a, TQ, smem, st) : launch_scan_K_MULTI_bf16(tmX, tmQ, a, TQ, smem, st);
+    case K_MULTI6: return f32 ? launch_scan_K_MULTI6_f32(tmX, tmQ, a, TQ, smem, st) : launch_scan_K_MULTI6_bf16(tmX, tmQ, a, TQ, smem, st);
     default: return cudaErrorInvalidValue;
   }
 }
 
 cudaError_t run_scan(const ScanPlan& pl, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D, int k,
-                     const MetricParams& mp, unsigned char* ws, float* out_all, cudaStream_t st) {
+                     const MetricParams& mp, unsigned char* ws, float* out_all, cudaStream_t st, const uint64_t* after, int kind_mask) {
   float* Qf = reinterpret_cast<float*>(ws + pl.off_qf);
   float* qn = reinterpret_cast<float*>(ws + pl.off_qn);
   cudaError_t e = launch_prep_queries(dtype, Q, int(nq), D, pl.nq_pad, pl.D_pad, Qf, qn, st);
@@ -63,9 +64,17 @@ cudaError_t run_scan(const ScanPlan& pl, int dtype, const void* Q, int64_t nq, c
   a.partial = reinterpret_cast<uint64_t*>(ws + pl.off_partial);
   a.out_all = out_all;
   a.mp = mp;
+  a.after = after;
+  a.nl = 1;
+  int kind = scan_kind_of(mp.metric);
+  if (kind_mask != 0) {
+    kind = K_MULTI6;
+    a.nl = 0;
+    for (int m = 0; m < RK_COUNT; ++m) a.lslot[m] = (kind_mask >> m) & 1 ? (signed char)(a.nl++) : (signed char)-1;
+  }
   CUtensorMap tmX, tmQ;
   setup_tma(a, dtype, pl.TQ, pl.nq_pad, pl.smem, &tmX, &tmQ);
-  return dispatch_scan(scan_kind_of(mp.metric), dtype == B200IR_F32, tmX, tmQ, a, pl.TQ, pl.smem, st);
+  return dispatch_scan(kind, dtype == B200IR_F32, tmX, tmQ, a, pl.TQ, pl.smem, st);
 }
 
 FallbackPlan make_fallback_plan(int dtype, int64_t nq, int64_t N, int D, int k) {
@@ -134,8 +143,9 @@ cudaError_t run_fallback(const FallbackPlan& fp, int dtype, const void* Q, int64
     setup_tma(a, dtype, 8, fp.count[t], fp.smem, &tmX, &tmQ);
     cudaError_t e = dispatch_scan(scan_kind_of(mp.metric), dtype == B200IR_F32, tmX, tmQ, a, 8, fp.smem, st);
     if (e != cudaSuccess) return e;
-    e = launch_finalize(a.partial, fp.count[t], int64_t(fp.P[t]) * k, k, mp, index_offset, out_score, out_idx, st,
-                        fb_list + fp.base[t], fb_count, fp.base[t]);
+    FinalizeOpts fo;
+    fo.qmap = fb_list + fp.base[t]; fo.gate = fb_count; fo.gate_base = fp.base[t];
+    e = launch_finalize(a.partial, fp.count[t], int64_t(fp.P[t]) * k, k, mp, index_offset, out_score, out_idx, st, fo);
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;

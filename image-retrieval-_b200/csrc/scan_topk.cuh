@@ -87,7 +87,7 @@ __device__ __noinline__ void compact_candidates(uint64_t* keys, int* cnt, uint64
 }
 
 template <int KIND>
-__device__ __forceinline__ void accum(float (&a)[(KIND == K_MULTI || KIND == K_EVAL) ? 4 : 1], float x, float q) {
+__device__ __forceinline__ void accum(float (&a)[(KIND == K_MULTI || KIND == K_EVAL || KIND == K_MULTI6) ? 4 : 1], float x, float q) {
   if constexpr (KIND == K_L1) a[0] += fabsf(x - q);
   else if constexpr (KIND == K_L2) { const float d = x - q; a[0] = fmaf(d, d, a[0]); }
   else if constexpr (KIND == K_LINF) a[0] = fmaxf(a[0], fabsf(x - q));
@@ -122,8 +122,9 @@ template <int KIND, typename T, int TQ>
 __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                  const __grid_constant__ CUtensorMap tmQ, const ScanArgs a) {
   constexpr int DKE = kRowChunkBytes / int(sizeof(T));     // elements of a row per pipeline step
-  constexpr int NA = (KIND == K_MULTI || KIND == K_EVAL) ? 4 : 1;
-  constexpr bool NEED_XSQ = (KIND == K_DOT || KIND == K_MULTI || KIND == K_EVAL);
+  constexpr int NA = (KIND == K_MULTI || KIND == K_EVAL || KIND == K_MULTI6) ? 4 : 1;
+  constexpr bool NEED_XSQ = (KIND == K_DOT || KIND == K_MULTI || KIND == K_EVAL || KIND == K_MULTI6);
+  const int NL = KIND == K_MULTI6 ? a.nl : 1;              // candidate lists per query
   constexpr int XT_BYTES = kScanThreads * kRowChunkBytes;  // 16 KB database tile per stage
   constexpr int QC_BYTES = TQ * DKE * 4;                   // fp32 query chunk per stage
   constexpr int STAGE_BYTES = XT_BYTES + (QC_BYTES + 1023) / 1024 * 1024;   // tiles stay 1024-byte aligned (TMA swizzle)
@@ -132,8 +133,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* stage_base = smem;
   uint64_t* keys_s = reinterpret_cast<uint64_t*>(smem + NST * STAGE_BYTES);
-  uint64_t* thr_s = keys_s + size_t(TQ) * a.sortn;
-  int* cnt_s = reinterpret_cast<int*>(thr_s + TQ);
+  uint64_t* thr_s = keys_s + size_t(TQ) * NL * a.sortn;
+  int* cnt_s = reinterpret_cast<int*>(thr_s + TQ * NL);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = blockIdx.x % a.G;
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
   const unsigned char* Xb = static_cast<const unsigned char*>(a.X);
   const int64_t row_bytes = int64_t(a.D) * int64_t(sizeof(T));
 
-  if (KIND != K_EVAL && tid < TQ) { thr_s[tid] = kKeyInf; cnt_s[tid] = 0; }
+  if (KIND != K_EVAL && tid < TQ * NL) { thr_s[tid] = kKeyInf; cnt_s[tid] = 0; }
 
   // Loader state advances incrementally (no divisions in the steady state).  Thread t copies the 16-byte
   // piece c = t & 7 of rows r0 + 16 i (r0 = t >> 3, i = 0..7): (r & 7) == (r0 & 7) for all of them, so the
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
   float qn[TQ];
 #pragma unroll
   for (int t = 0; t < TQ; ++t) qn[t] = a.qnorm[g * TQ + t];
+  const bool paged = a.after != nullptr;                   // paging: candidates must sort strictly after the query's cursor
 
   int tile = 0, chunk = 0, stage = 0;
   for (int it = 0; it < total; ++it) {
@@ -384,15 +386,40 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
           }
         } else
         if (valid && q < nq_eff) {
+          if constexpr (KIND == K_MULTI6) {
+            // all six rankings of this (query, row) pair from the four accumulators (geometric_metrics.py:12-57, :85-92)
+            const float xn = sqrtf(xsq);
+            float cs = 0.f;
+            if (qn[t] != 0.f && xn != 0.f) cs = acc[t][0] / (qn[t] * xn);
+            const float fD = float(a.mp.D);
+            const float mag = fabsf(qn[t] - xn);
+            float sim = a.mp.w[0] * cs - a.mp.w[1] * (acc[t][1] / fD) - a.mp.w[2] * (sqrtf(acc[t][2]) / sqrtf(fD)) - a.mp.w[3] * acc[t][3] -
+                        a.mp.w[4] * mag;
+            if (a.mp.flags & B200IR_FLAG_ABS_SCORE) { cs = fabsf(cs); sim = fabsf(sim); }
+            const float rk[RK_COUNT] = {-cs, acc[t][1], acc[t][2], acc[t][3], mag, -sim};
+#pragma unroll
+            for (int m = 0; m < RK_COUNT; ++m) {
+              const int ls = a.lslot[m];
+              if (ls >= 0) {
+                const int L = t * NL + ls;
+                const uint64_t key = make_key(rk[m], uint32_t(grow));
+                if (key < thr_s[L]) {
+                  const int slot = atomicAdd(&cnt_s[L], 1);
+                  keys_s[size_t(L) * a.sortn + slot] = key;
+                }
+              }
+            }
+          } else {
           const float r = finish_rank<KIND>(acc[t], xsq, qn[t], a.mp);
           if (topk_mode) {
             const uint64_t key = make_key(r, uint32_t(grow));
-            if (key < thr_s[t]) {
+            if (key < thr_s[t] && (!paged || key > a.after[g * TQ + t])) {     // cursor read only on the (rare) hit path
               const int slot = atomicAdd(&cnt_s[t], 1);
               keys_s[size_t(t) * a.sortn + slot] = key;
             }
           } else {
             a.out_all[int64_t(q) * a.N + grow] = rank_to_score(r, a.mp.metric, a.mp.flags, a.mp.D);
+          }
           }
         }
 #pragma unroll
@@ -404,7 +431,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
       }
       if (KIND != K_EVAL && topk_mode) {
         __syncthreads();
-        for (int t = warp; t < TQ; t += kScanThreads / 32) {
+        for (int t = warp; t < TQ * NL; t += kScanThreads / 32) {
           if (cnt_s[t] > a.sortn - kScanThreads) {
             if (a.sortn == 256) compact_candidates<8>(keys_s + size_t(t) * a.sortn, &cnt_s[t], &thr_s[t], a.k, lane);
             else compact_candidates<16>(keys_s + size_t(t) * a.sortn, &cnt_s[t], &thr_s[t], a.k, lane);
@@ -424,14 +451,15 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
   }
   if (topk_mode) {
     __syncthreads();
-    for (int t = warp; t < TQ; t += kScanThreads / 32) {
+    for (int L = warp; L < TQ * NL; L += kScanThreads / 32) {
+      const int t = L / NL, ls = L % NL;
       const int q = g * TQ + t;
       if (q >= nq_eff) continue;
-      uint64_t* kb = keys_s + size_t(t) * a.sortn;
-      if (a.sortn == 256) compact_candidates<8>(kb, &cnt_s[t], &thr_s[t], a.k, lane);
-      else compact_candidates<16>(kb, &cnt_s[t], &thr_s[t], a.k, lane);
-      const int kept = cnt_s[t];
-      uint64_t* dst = a.partial + (int64_t(q) * a.P + p) * a.k;
+      uint64_t* kb = keys_s + size_t(L) * a.sortn;
+      if (a.sortn == 256) compact_candidates<8>(kb, &cnt_s[L], &thr_s[L], a.k, lane);
+      else compact_candidates<16>(kb, &cnt_s[L], &thr_s[L], a.k, lane);
+      const int kept = cnt_s[L];
+      uint64_t* dst = a.partial + ((int64_t(ls) * a.nq + q) * a.P + p) * a.k;      // [nl][nq][P][k]
       for (int i = lane; i < a.k; i += 32) dst[i] = i < kept ? kb[i] : kKeyInf;
     }
   }

@@ -45,17 +45,39 @@ __device__ __forceinline__ void emit_topk(uint64_t (&r)[E], int lane, int k, con
 
 // One warp per query: stream P*k sorted-or-not keys through a 32*E-wide bitonic sorter, keeping
 // the best k between rounds.  Writes the reference-normalised score and the global index.
-// qmap / gate (both nullptr for a plain search): the launch finishes positions [0, min(nq, *gate - gate_base)) of a
-// device-side query list and writes row qmap[q] of the outputs (fallback of the tensor path).
+// Options of the final merge.
+//   qmap / gate: the launch finishes positions [0, min(nq, *gate - gate_base)) of a device-side query list and writes
+//                row qmap[q] of the outputs (fallback of the tensor path).
+//   last_key:    paging cursor out, the rank key of the k-th winner of each query (kKeyInf: the store is exhausted).
+//   nmetrics>0:  multi-list scan; blockIdx.y = requested metric y, which reads list slot[y] ([nl][nq][P][k] keys,
+//                list_stride apart), applies metric[y]'s score transform and writes plane y of the outputs.
+struct FinalizeOpts {
+  const int* qmap = nullptr;
+  const int* gate = nullptr;
+  int gate_base = 0;
+  uint64_t* last_key = nullptr;
+  int nmetrics = 0;
+  signed char slot[B200IR_NUM_METRICS] = {0};
+  signed char metric[B200IR_NUM_METRICS] = {0};
+  int64_t list_stride = 0, out_stride = 0;
+};
+
 template <int E>
 __global__ void __launch_bounds__(128) finalize_topk_kernel(const uint64_t* __restrict__ partial, int nq, int64_t per_query,
                                                            int k, MetricParams mp, int64_t index_offset,
                                                            float* __restrict__ out_score, int64_t* __restrict__ out_idx,
-                                                           const int* __restrict__ qmap, const int* __restrict__ gate, int gate_base) {
+                                                           const FinalizeOpts o) {
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (q >= nq) return;
-  if (gate != nullptr && q >= *gate - gate_base) return;
+  if (o.gate != nullptr && q >= *o.gate - o.gate_base) return;
+  if (o.nmetrics > 0) {
+    const int y = blockIdx.y;
+    partial += int64_t(o.slot[y]) * o.list_stride;
+    out_score += int64_t(y) * o.out_stride;
+    out_idx += int64_t(y) * o.out_stride;
+    mp.metric = o.metric[y];
+  }
   const uint64_t* src = partial + int64_t(q) * per_query;
   uint64_t r[E];
 #pragma unroll
@@ -75,7 +97,11 @@ __global__ void __launch_bounds__(128) finalize_topk_kernel(const uint64_t* __re
     warp_sort<E>(r, lane);
     kept = k;
   } while (pos < per_query);
-  emit_topk<E>(r, lane, k, mp, index_offset, out_score, out_idx, qmap != nullptr ? int64_t(qmap[q]) : int64_t(q));
+  if (o.last_key != nullptr) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) if (lane * E + e == k - 1) o.last_key[q] = r[e];
+  }
+  emit_topk<E>(r, lane, k, mp, index_offset, out_score, out_idx, o.qmap != nullptr ? int64_t(o.qmap[q]) : int64_t(q));
 }
 
 // Cross-shard merge: score/idx lists of R shards -> [nq, k] ordered by (score, global idx).
@@ -176,11 +202,11 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(int descending, const f
 
 inline cudaError_t launch_finalize(const uint64_t* partial, int64_t nq, int64_t per_query, int k, const MetricParams& mp,
                                    int64_t index_offset, float* out_score, int64_t* out_idx, cudaStream_t st,
-                                   const int* qmap = nullptr, const int* gate = nullptr, int gate_base = 0) {
-  const int blocks = int(ceil_div64(nq, 4));
+                                   const FinalizeOpts& o = FinalizeOpts()) {
+  const dim3 grid(unsigned(ceil_div64(nq, 4)), unsigned(o.nmetrics > 0 ? o.nmetrics : 1));
   ProfileScope ps(PT_FINALIZE, st);
-  if (k <= 128) finalize_topk_kernel<8><<<blocks, 128, 0, st>>>(partial, int(nq), per_query, k, mp, index_offset, out_score, out_idx, qmap, gate, gate_base);
-  else finalize_topk_kernel<16><<<blocks, 128, 0, st>>>(partial, int(nq), per_query, k, mp, index_offset, out_score, out_idx, qmap, gate, gate_base);
+  if (k <= 128) finalize_topk_kernel<8><<<grid, 128, 0, st>>>(partial, int(nq), per_query, k, mp, index_offset, out_score, out_idx, o);
+  else finalize_topk_kernel<16><<<grid, 128, 0, st>>>(partial, int(nq), per_query, k, mp, index_offset, out_score, out_idx, o);
   return cudaGetLastError();
 }
 

@@ -20,6 +20,15 @@ def _one(metric, vec1, vec2, **kw):
     return np.float32(ops.pairwise(_vec(vec1), _vec(vec2), metric, **kw).item())
 
 
+def _seven(vec1, vec2):
+    """The seven get_all_metrics values of one pair from ONE kernel launch and one device->host copy
+    (b200ir_pair_metrics), as np.float32 in ops.PAIR_METRICS order."""
+    a, b = _vec(vec1), _vec(vec2)
+    if a.shape[1] != b.shape[1]:
+        raise ValueError(f"operands could not be broadcast together with shapes ({a.shape[1]},) ({b.shape[1]},)")
+    return ops.pair_metrics(a, b, [0], [0]).cpu().numpy()[:, 0]
+
+
 class GeometricSimilarityMetrics:
     """Class implementing various geometric similarity metrics for embeddings."""
 
@@ -38,10 +47,8 @@ class GeometricSimilarityMetrics:
     @staticmethod
     def cosine_similarity(vec1: np.ndarray, vec2: np.ndarray) -> float:
         """Computes the cosine similarity between two vectors (geometric_metrics.py:12-18)."""
-        sq = ops.row_sqnorms(np.concatenate([_vec(vec1), _vec(vec2)])).cpu().numpy()
-        if sq[0] == 0 or sq[1] == 0:
-            return 0.0
-        return _one("cosine_similarity", vec1, vec2)
+        c = _seven(vec1, vec2)[0]             # zero norm -> 0.0 inside the kernel (:16-17)
+        return 0.0 if c == 0 else c           # the reference's zero-norm branch returns the Python float 0.0
 
     @staticmethod
     def angular_distance(vec1: np.ndarray, vec2: np.ndarray) -> float:
@@ -96,15 +103,15 @@ class GeometricSimilarityMetrics:
     @staticmethod
     def get_all_metrics(vec1: np.ndarray, vec2: np.ndarray) -> Dict[str, float]:
         """All seven metrics between two vectors (geometric_metrics.py:114-129)."""
-        G = GeometricSimilarityMetrics
+        v = _seven(vec1, vec2)                # one launch for all seven values (the reference recomputes cos 3x, norms 8x)
         return {
-            'cosine_similarity': G.cosine_similarity(vec1, vec2),
-            'cosine_distance': G.cosine_distance(vec1, vec2),
-            'angular_distance': G.angular_distance(vec1, vec2),
-            'l1_distance': G.l1_distance(vec1, vec2),
-            'l2_distance': G.l2_distance(vec1, vec2),
-            'linf_distance': G.linf_distance(vec1, vec2),
-            'magnitude_difference': G.magnitude_difference(vec1, vec2)
+            'cosine_similarity': v[0],
+            'cosine_distance': v[1],
+            'angular_distance': v[2],
+            'l1_distance': v[3],
+            'l2_distance': np.float64(v[4]),   # the reference's l2 is fp32 / np.sqrt(int) -> float64 (:46)
+            'linf_distance': v[5],
+            'magnitude_difference': v[6]
         }
 
     @staticmethod

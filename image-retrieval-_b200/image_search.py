@@ -68,7 +68,7 @@ class EnhancedTextImageSearcher:
             raise RuntimeError("EnhancedTextImageSearcher has no collection")
         if isinstance(c, tuple):
             paths, m = c
-            return list(paths), ops.as_device_matrix(m)
+            return (paths if isinstance(paths, list) else list(paths)), ops.as_device_matrix(m)
         return c.paths, c.device_matrix()
 
     def _candidates(self, q, limit):
@@ -76,10 +76,11 @@ class EnhancedTextImageSearcher:
         paths, X = self._store()
         if X is None or len(paths) == 0:
             return paths, None, None, None
-        k = max(1, min(int(limit), len(paths), ops.MAX_K))
+        k = max(1, min(int(limit), len(paths)))       # limit = 3 * top_k / 5 * top_k as in the reference; paged beyond MAX_K
+        if k > ops.MAX_K_PAGED:
+            raise ValueError(f"candidate lists hold up to {ops.MAX_K_PAGED} rows, asked for {limit}")
         s, i = ops.topk(q, X, "cosine_similarity", k)
-        keep = i[0] >= 0
-        return paths, X, s[0][keep], i[0][keep]
+        return paths, X, s[0], i[0]                   # k <= N: no padding entries
 
     def search(self, text_query, top_k: int = 5, score_threshold: float = SCORE_THRESHOLD,
                use_optimized_similarity: bool = False):
@@ -89,12 +90,10 @@ class EnhancedTextImageSearcher:
         if idx is None or idx.numel() == 0:
             return []
         if use_optimized_similarity:
-            cand = X.index_select(0, idx)
-            n = cand.shape[0]
-            s, j = ops.topk(q, cand, "optimized_similarity", n, params=self.similarity_params)
-            order = j[0]
-            scores = s[0].cpu().numpy()
-            rows = idx[order].cpu().numpy()
+            # :103-107 + :115: optimized score of every candidate, stable sort descending - two launches on the device
+            self._check_rerank_limit(idx.numel(), "search(use_optimized_similarity=True)")
+            r = ops.rank_candidates(q, X, idx.view(1, -1), idx.numel(), params=self.similarity_params)
+            scores, rows = r["val"][5, 0].cpu().numpy(), r["row"][5, 0].cpu().numpy()
         else:
             scores, rows = cos.cpu().numpy(), idx.cpu().numpy()
         matches = [{"path": paths[r], "score": sc} for sc, r in zip(scores, rows)]   # already sorted desc, stable
@@ -115,9 +114,19 @@ class EnhancedTextImageSearcher:
         logger.info(f"Found {len(unique)} matches")
         return unique[:top_k]
 
+    @staticmethod
+    def _check_rerank_limit(kc, what):
+        if kc > ops.MAX_CANDIDATES:
+            raise ValueError(f"{what}: the candidate list ({kc} rows) exceeds the {ops.MAX_CANDIDATES} rows the re-ranking "
+                             f"kernel holds (top_k up to {ops.MAX_CANDIDATES // 3} for search, {ops.MAX_CANDIDATES // 5} for "
+                             "search_with_multiple_metrics)")
+
     def _path_groups(self, paths):
-        """(N,) int64 device tensor: rows holding the same path share an id (what `seen_paths` compares, :128-137)."""
-        key = (id(paths), len(paths))
+        """(N,) int64 device tensor: rows holding the same path share an id (what `seen_paths` compares, :128-137).
+        Cached per collection OBJECT and its mutation counter (EmbeddingStore.version); a (paths, matrix) tuple is
+        keyed by the tuple itself and the identity of its path list, never by the address of a temporary."""
+        c = self.collection
+        key = (id(c), getattr(c, "version", None), id(c[0]) if isinstance(c, tuple) else None, len(paths))
         if getattr(self, "_groups_key", None) != key:
             first = {}
             ids = np.fromiter((first.setdefault(p, i) for i, p in enumerate(paths)), dtype=np.int64, count=len(paths))
@@ -133,19 +142,14 @@ class EnhancedTextImageSearcher:
         paths, X = self._store()
         if X is None or len(paths) == 0:
             return [[] for _ in range(Q.shape[0])]
-        kc = max(1, min(int(top_k) * 3, len(paths), ops.MAX_K))
+        kc = max(1, min(int(top_k) * 3, len(paths)))
+        self._check_rerank_limit(kc, "search_batch")                      # the post-filter kernel holds the same 1024 rows
         s, i = ops.topk(Q, X, "cosine_similarity", kc)                    # candidate stage (:88-95)
         if use_optimized_similarity:
-            # re-score the cosine candidates (:103-107) from one get_all_metrics launch, then the stable sort of :116
-            nq = Q.shape[0]
-            qi = torch.arange(nq, device=i.device).repeat_interleave(kc)
-            v = ops.pair_metrics(Q, X, qi, i.reshape(-1))
-            w = dict(w_angle=1.0, w_l1=0.0, w_l2=0.0, w_inf=0.0, w_mag=0.0)
-            w.update(self.similarity_params or {})
-            sim = (w["w_angle"] * v[0] - w["w_l1"] * v[3] - w["w_l2"] * v[4] - w["w_inf"] * v[5] - w["w_mag"] * v[6]).view(nq, kc)
-            sim = torch.where(i >= 0, sim, torch.full_like(sim, float("-inf")))
-            s, order = torch.sort(sim, dim=1, descending=True, stable=True)
-            i = torch.gather(i, 1, order)
+            # re-score the cosine candidates (:103-107) and stable-sort them (:115) on the device: get_all_metrics of every
+            # (query, candidate) pair in one launch, weighted sum + ordering in a second one
+            r = ops.rank_candidates(Q, X, i, kc, params=self.similarity_params)
+            s, i = r["val"][5], r["row"][5]
         fs, fi, cnt = ops.threshold_dedupe(s, i, int(top_k), score_threshold, relative=use_optimized_similarity,
                                            group=self._path_groups(paths))
         fs, fi, cnt = fs.cpu().numpy(), fi.cpu().numpy(), cnt.cpu().numpy()
@@ -161,23 +165,22 @@ class EnhancedTextImageSearcher:
             out = {n: [] for n in names if n != "angular_distance"}
             out["analysis"] = self._analyze_metric_results(out)
             return out
-        cand = X.index_select(0, idx)
+        # :173-219 on the device: all seven metric values of every candidate from ONE launch, the weighted score and the six
+        # stable orderings from a second one (the reference makes ~10 Python metric calls per candidate and six sorts)
+        kc = idx.numel()
+        self._check_rerank_limit(kc, "search_with_multiple_metrics")
+        k = min(max(0, int(top_k)), kc)
+        r = ops.rank_candidates(q, X, idx.view(1, -1), max(k, 1), params=self.similarity_params)
         rows = idx.cpu().numpy()
-        table = {}
-        for n in names:
-            kw = {"params": self.similarity_params} if n == "optimized_similarity" else {}
-            table[n] = ops.pairwise(q, cand, n, **kw)[0].cpu().numpy()
-        candidates = [dict({"path": paths[rows[c]]}, **{n: table[n][c] for n in names}) for c in range(len(rows))]
-        k = min(max(0, int(top_k)), len(rows))
+        vals = r["metrics"][:, 0].cpu().numpy()
+        opt = r["optimized"][0].cpu().numpy()
+        table = {n: vals[y] for y, n in enumerate(ops.PAIR_METRICS)}
+        table["optimized_similarity"] = opt
+        candidates = [dict({"path": paths[rows[c]]}, **{n: table[n][c] for n in names}) for c in range(kc)]
+        pos = r["pos"][:, 0].cpu().numpy()
         metric_results = {}
-        for n in ("cosine_similarity", "l1_distance", "l2_distance", "linf_distance", "magnitude_difference",
-                  "optimized_similarity"):
-            kw = {"params": self.similarity_params} if n == "optimized_similarity" else {}
-            if k == 0:
-                metric_results[n] = []
-                continue
-            _s, j = ops.topk(q, cand, n, k, **kw)                 # fused ranking over the candidate rows
-            metric_results[n] = [candidates[c] for c in j[0].cpu().numpy() if c >= 0]
+        for y, n in enumerate(ops.RANK_ORDERINGS):
+            metric_results[n] = [candidates[c] for c in pos[y][:k] if c >= 0] if k > 0 else []
         metric_results["analysis"] = self._analyze_metric_results(metric_results)
         return metric_results
 

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import (ANGLE, BF16, COS_DIST, COS_SIM, F32, FLAG_ABS_SCORE, FLAG_HAVE_INDEX, FLAG_NO_RERANK, FLAG_NO_TENSOR,
-                   FLAG_RAW, HSV, L1, L2, LINF, MAG_DIFF, MAX_K, OPTIMIZED, RGB, B200IRError)
+                   FLAG_RAW, HSV, L1, L2, LINF, MAG_DIFF, MAX_CANDIDATES, MAX_K, MAX_K_PAGED, OPTIMIZED, RGB, B200IRError)
 
 METRIC_IDS = {
     "l1": L1, "l1_distance": L1,
@@ -173,12 +173,16 @@ def topk(Q, X, metric, k, *, index_offset=0, normalized=True, abs_score=False, p
     Q = as_device_matrix(Q, dtype=X.dtype)
     if Q.shape[1] != X.shape[1]:
         raise ValueError(f"dimension mismatch: queries {Q.shape[1]} vs database {X.shape[1]}")
-    if not 1 <= k <= MAX_K:
-        raise ValueError(f"k must be in 1..{MAX_K}")
+    if not 1 <= k <= MAX_K_PAGED:
+        raise ValueError(f"k must be in 1..{MAX_K_PAGED} (one page holds {MAX_K}; longer lists are served page by page)")
     lib = _lib.load()
     nq, D = Q.shape
     N = X.shape[0]
     f = _flags(normalized, abs_score, flags)
+    if k > MAX_K:
+        if out is not None:
+            raise ValueError("out= is not supported for paged result lists (k > %d)" % MAX_K)
+        return _topk_paged(lib, m, Q, X, k, int(index_offset), f, params)
     if out is None:
         scores = torch.empty((nq, k), dtype=torch.float32, device=X.device)
         idx = torch.empty((nq, k), dtype=torch.int64, device=X.device)
@@ -204,6 +208,99 @@ def topk(Q, X, metric, k, *, index_offset=0, normalized=True, abs_score=False, p
 
 
 _last_topk = None
+
+
+def _topk_paged(lib, m, Q, X, k, index_offset, f, params):
+    """k > MAX_K: exact result pages of MAX_K through the CUDA-core scan with a per-query cursor (every page continues
+    strictly after the previous page's last rank key), then one (score, index) ordering of the concatenated rows."""
+    nq, D = Q.shape
+    N = X.shape[0]
+    scores = torch.empty((nq, k), dtype=torch.float32, device=X.device)
+    idx = torch.empty((nq, k), dtype=torch.int64, device=X.device)
+    if nq == 0:
+        return scores, idx
+    if N == 0:
+        scores.fill_(float("-inf") if m in DESCENDING else float("inf"))
+        idx.fill_(-1)
+        return scores, idx
+    cursors = [torch.empty(nq, dtype=torch.int64, device=X.device) for _ in range(2)]
+    need = lib.b200ir_topk_workspace_bytes(m, _dtype_id(X), nq, N, D, MAX_K, f | FLAG_NO_TENSOR)
+    ws = _workspace(need, X.device)
+    done, page = 0, 0
+    while done < k:
+        kk = min(MAX_K, k - done)
+        ps = torch.empty((nq, kk), dtype=torch.float32, device=X.device)
+        pi = torch.empty((nq, kk), dtype=torch.int64, device=X.device)
+        after = _ptr(cursors[(page + 1) % 2]) if page > 0 else None
+        st = lib.b200ir_topk_paged(m, _dtype_id(X), _ptr(Q), nq, _ptr(X), N, D, kk, index_offset, f, _weights(params), after,
+                                   _ptr(cursors[page % 2]), _ptr(ps), _ptr(pi), _ptr(ws), ws.numel(), _stream())
+        _lib.check(st, "topk_paged")
+        scores[:, done:done + kk] = ps
+        idx[:, done:done + kk] = pi
+        done += kk
+        page += 1
+    _lib.check(lib.b200ir_sort_topk_rows(1 if m in DESCENDING else 0, _ptr(scores), _ptr(idx), nq, k, _stream()), "sort_topk_rows")
+    return scores, idx
+
+
+def topk_multi(Q, X, metrics, k, *, index_offset=0, normalized=True, abs_score=False, params=None):
+    """Top-k under SEVERAL metrics from ONE pass over the store (b200ir_topk_multi; replaces the three scans of
+    app_pipeline.py:296-328).  Returns (scores (M, nq, k), indices (M, nq, k)), plane y = metrics[y]."""
+    ids = [metric_id(mm) for mm in metrics]
+    if isinstance(X, PreparedIndex):
+        X = X.X
+    else:
+        X = as_device_matrix(X)
+    Q = as_device_matrix(Q, dtype=X.dtype)
+    if Q.shape[1] != X.shape[1]:
+        raise ValueError(f"dimension mismatch: queries {Q.shape[1]} vs database {X.shape[1]}")
+    if not 1 <= k <= MAX_K:
+        raise ValueError(f"topk_multi: k must be in 1..{MAX_K}")
+    lib = _lib.load()
+    nq, D = Q.shape
+    N = X.shape[0]
+    M = len(ids)
+    arr = (ctypes.c_int * M)(*ids)
+    scores = torch.empty((M, nq, k), dtype=torch.float32, device=X.device)
+    idx = torch.empty((M, nq, k), dtype=torch.int64, device=X.device)
+    if nq == 0:
+        return scores, idx
+    need = lib.b200ir_topk_multi_workspace_bytes(arr, M, _dtype_id(X), nq, max(N, 1), D, k)
+    ws = _workspace(need, X.device)
+    st = lib.b200ir_topk_multi(arr, M, _dtype_id(X), _ptr(Q), nq, _ptr(X), N, D, k, int(index_offset), _flags(normalized, abs_score, 0),
+                               _weights(params), _ptr(scores), _ptr(idx), _ptr(ws), ws.numel(), _stream())
+    _lib.check(st, "topk_multi")
+    return scores, idx
+
+
+RANK_ORDERINGS = ("cosine_similarity", "l1_distance", "l2_distance", "linf_distance", "magnitude_difference", "optimized_similarity")
+
+
+def rank_candidates(Q, X, cand_idx, k, params=None):
+    """Re-ranking of per-query candidate lists (image_search.py:98-115, :173-219): the seven get_all_metrics values of
+    every (query, candidate) pair from one launch, the weighted optimized score, and the six stable per-metric
+    orderings from a second one.  cand_idx (nq, kc) int64 rows, -1 = padding.  Returns a dict of device tensors:
+    metrics (7, nq, kc) in PAIR_METRICS order, optimized (nq, kc), pos / val / row (6, nq, k) in RANK_ORDERINGS order."""
+    X = X.X if isinstance(X, PreparedIndex) else as_device_matrix(X)
+    Q = as_device_matrix(Q, dtype=X.dtype)
+    cand_idx = cand_idx.contiguous()
+    nq, kc = cand_idx.shape
+    if Q.shape[0] != nq:
+        raise ValueError("rank_candidates: one candidate list per query")
+    if not 1 <= kc <= MAX_CANDIDATES:
+        raise ValueError(f"rank_candidates: candidate lists hold 1..{MAX_CANDIDATES} rows")
+    k = max(1, min(int(k), kc))
+    lib = _lib.load()
+    vals = torch.empty((len(PAIR_METRICS), nq, kc), dtype=torch.float32, device=X.device)
+    _lib.check(lib.b200ir_candidate_metrics(_dtype_id(X), _ptr(Q), nq, _ptr(X), X.shape[0], X.shape[1], _ptr(cand_idx), kc, _ptr(vals),
+                                            _stream()), "candidate_metrics")
+    opt = torch.empty((nq, kc), dtype=torch.float32, device=X.device)
+    pos = torch.empty((6, nq, k), dtype=torch.int32, device=X.device)
+    val = torch.empty((6, nq, k), dtype=torch.float32, device=X.device)
+    row = torch.empty((6, nq, k), dtype=torch.int64, device=X.device)
+    _lib.check(lib.b200ir_rank_candidates(_ptr(vals), _ptr(cand_idx), nq, kc, _weights(params), k, _ptr(opt), _ptr(pos), _ptr(val),
+                                          _ptr(row), _stream()), "rank_candidates")
+    return {"metrics": vals, "optimized": opt, "pos": pos, "val": val, "row": row}
 
 
 def last_fallback_count():

@@ -19,6 +19,7 @@ class EmbeddingStore:
         self.magnitudes = None      # (N,) CUDA fp32 or None
         self._pending = []          # host rows not yet uploaded
         self._pending_mag = []
+        self.version = 0            # bumped whenever rows / paths change: keys the caches built on top of the store
 
     def __len__(self):
         return len(self.paths)
@@ -30,6 +31,7 @@ class EmbeddingStore:
         if v.shape[0] != self.dim:
             raise ValueError(f"embedding dimension {v.shape[0]} != store dimension {self.dim}")
         self.paths.append(str(path))
+        self.version += 1
         self._pending.append(v)
         self._pending_mag.append(1.0 if magnitude is None else float(magnitude))
 
@@ -44,6 +46,7 @@ class EmbeddingStore:
         mag = torch.ones(m.shape[0], dtype=torch.float32, device=m.device) if magnitudes is None else \
             torch.as_tensor(magnitudes, dtype=torch.float32).to(m.device)
         self.paths.extend(str(p) for p in paths)
+        self.version += 1
         self.matrix = m if self.matrix is None else torch.cat([self.matrix, m])
         self.magnitudes = mag if self.magnitudes is None else torch.cat([self.magnitudes, mag])
 
@@ -59,3 +62,8 @@ class EmbeddingStore:
 
     def device_matrix(self):
         return self.flush()
+
+    def set_path(self, row, path):
+        """Rename a stored row (keeps the de-duplication groups of the searchers in step)."""
+        self.paths[row] = str(path)
+        self.version += 1

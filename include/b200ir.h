@@ -130,6 +130,49 @@ int b200ir_topk_indexed(int metric, int dtype, const void* Q, int64_t nq, const 
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Result pages beyond B200IR_MAX_K.  The reference returns results[:top_k] for ANY top_k (app_pipeline.py:172) and
+ * fetches 3 * top_k / 5 * top_k candidates (image_search.py:92, :169).  b200ir_topk_paged is b200ir_topk's exact
+ * CUDA-core scan with a cursor: `after` [nq] (NULL for the first page) holds each query's last rank key of the
+ * previous page and only rows that sort strictly after it are candidates; `last` [nq] receives the cursor of this
+ * page (all-ones when the store is exhausted).  Workspace: b200ir_topk_workspace_bytes(..., flags | NO_TENSOR).
+ * Pages are concatenated by the caller; b200ir_sort_topk_rows then orders each row of score / idx [nq][K] (K <= 4096)
+ * by (score, index) in place - distinct rank values can round to one fp32 score across a page boundary, and the
+ * reference's stable sort orders equal scores by index.
+ */
+int b200ir_topk_paged(int metric, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D, int k,
+                      int64_t index_offset, int flags, const float* weights_host, const uint64_t* after, uint64_t* last,
+                      float* out_score, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+int b200ir_sort_topk_rows(int descending, float* score, int64_t* idx, int64_t nq, int K, void* stream);
+
+/*
+ * Several metrics from ONE pass over the store: replaces the three scans + three sorts of
+ * EnhancedImageSearchApp.search_with_multiple_metrics (app_pipeline.py:296-328).  The scan keeps one candidate list per
+ * requested ranking (dot, sum|d|, sum d^2, max|d| and the norms are accumulated together; cosine similarity /
+ * distance / angle share the descending-cosine list) and writes out_score / out_idx [nmetrics][nq][k], plane y holding
+ * metric metrics_host[y] with b200ir_topk's contract.  weights_host feeds B200IR_OPTIMIZED (defaults when NULL).
+ */
+size_t b200ir_topk_multi_workspace_bytes(const int* metrics_host, int nmetrics, int dtype, int64_t nq, int64_t N, int D, int k);
+int b200ir_topk_multi(const int* metrics_host, int nmetrics, int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D,
+                      int k, int64_t index_offset, int flags, const float* weights_host, float* out_score, int64_t* out_idx,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Re-ranking of candidate lists (image_search.py:98-115 and :173-219).  pair_vals [7][nq * kc] are the get_all_metrics
+ * values of the pairs (query q, candidate c) as b200ir_pair_metrics writes them; cand_idx [nq][kc] the candidates'
+ * rows, -1 = padding (kc <= 1024).  out_optimized [nq][kc] (may be NULL) receives w_angle*cos - w_l1*L1 - w_l2*L2 -
+ * w_inf*Linf - w_mag*mag of every candidate (geometric_metrics.py:85-92); for each ordering y = 0 cosine desc, 1 l1,
+ * 2 l2, 3 linf, 4 magnitude (ascending), 5 optimized desc, the first k entries of the stably sorted candidate list
+ * (ties keep candidate order, like list.sort) go to out_pos (position in the list), out_val (the sort value) and
+ * out_row (database row), each [6][nq][k], padding -1 / NaN / -1.
+ */
+/* get_all_metrics of every (query q, candidate cand_idx[q][c]) pair: b200ir_pair_metrics with the query index implied;
+ * out [7][nq * kc], NaN for padding candidates (cand_idx < 0). */
+int b200ir_candidate_metrics(int dtype, const void* Q, int64_t nq, const void* X, int64_t N, int D, const int64_t* cand_idx, int kc,
+                             float* out, void* stream);
+int b200ir_rank_candidates(const float* pair_vals, const int64_t* cand_idx, int64_t nq, int kc, const float* weights_host, int k,
+                           float* out_optimized, int32_t* out_pos, float* out_val, int64_t* out_row, void* stream);
+
+/*
  * Full (nq, N) metric matrix, same arithmetic as b200ir_topk's CUDA-core scan.
  * Replaces the pair loops of mi_analysis.py:277-292 / get_all_metrics
  * (geometric_metrics.py:114-129) for evaluation-sized inputs.
