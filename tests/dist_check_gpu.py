@@ -1,5 +1,6 @@
 """Multi-GPU check (run under torchrun on a GPU box): the row-sharded search over NCCL equals the single-GPU search
-exactly, for a tensor-core metric and a scan metric.  Not collected by pytest (needs >= 2 GPUs):
+exactly, for tensor-core metrics (bf16 and fp32 stores) and scan metrics.  tests/test_gpu_dist.py launches it when the
+box has >= 2 GPUs; by hand:
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_check_gpu.py
 """
 import os
@@ -26,6 +27,7 @@ def main():
     b, e = shard_range(N, world, rank)
     ok = True
     for dtype, metric, k in ((torch.bfloat16, "cosine_similarity", 100), (torch.bfloat16, "l2", 10),
+                             (torch.float32, "cosine_similarity", 100), (torch.float32, "l2", 10),      # fp32 store on the tensor path
                              (torch.float32, "l1", 10), (torch.float32, "linf", 7)):
         Xd, Qd = X.to(dtype), Q.to(dtype)
         s1, i1 = ops.topk(Qd, Xd, metric, k)

@@ -1,5 +1,5 @@
-"""world_size-2 / -3 gloo test of the row-sharded search: shard ranges, index offsets, the single
-all-gather and the merge order.  The local search and the merge are the oracle here (this is a
+"""world_size-2 / -3 gloo test of the row-sharded search: shard ranges, index offsets, the all-to-all of
+query slices, the merge order and the final all-gather.  The local search and the merge are the oracle here (this is a
 CPU test of the host logic; the CUDA operators are covered by -m gpu tests)."""
 import os
 import socket
@@ -51,9 +51,14 @@ def _worker(rank, world, port, out_dir):
     b, e = shard_range(len(X), world, rank)
     index = ShardedIndex(X[b:e], b, local_topk=local_topk, merge=merge)
     res = {}
+    from image_retrieval_b200.sharded import query_slice
     for metric in ("l1", "cosine_similarity"):
         s, i = index.topk(Q, metric, 9)
         res[metric] = (s.numpy(), i.numpy())
+        # the slice every rank serves on its own (no final all-gather) is the matching rows of the full result
+        ss, si, q0, q1 = index.topk_slice(Q, metric, 9)
+        assert (q0, q1) == query_slice(len(Q), world, rank)
+        assert np.array_equal(si.numpy()[:q1 - q0], i.numpy()[q0:q1]) and np.array_equal(ss.numpy()[:q1 - q0], s.numpy()[q0:q1])
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **{f"{m}_{n}": a for m, (s, i) in res.items() for n, a in (("s", s), ("i", i))})
     dist.barrier()
     dist.destroy_process_group()
