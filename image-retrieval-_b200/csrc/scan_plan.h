@@ -78,8 +78,8 @@ constexpr int kEvalMetrics = 5;    // cosine_distance, l1, l2, linf, magnitude_d
 constexpr int kEvalTQ = 8;
 // one pipeline stage: 16 KB database tile + the fp32 query chunk, padded so that every tile stays 1024-byte aligned
 // (required by the 128-byte TMA swizzle)
-inline size_t scan_stage_bytes(int TQ, int DKE) {
-  return size_t(kScanThreads) * kRowChunkBytes + size_t(round_up64(size_t(TQ) * DKE * 4, 1024));
+inline size_t scan_stage_bytes(int TQ, int DKE, int TR = 1) {
+  return size_t(kScanThreads) * TR * kRowChunkBytes + size_t(round_up64(size_t(TQ) * DKE * 4, 1024));
 }
 // density bins in shared memory: 16-bit counters, two per 32-bit word
 __host__ __device__ inline int eval_hist_words(int nbins) { return (kEvalMetrics * 4 * nbins + 1) / 2; }
@@ -90,7 +90,7 @@ inline size_t eval_smem_bytes(int nbins, int nthr) {
 cudaError_t launch_scan_eval_f32(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, size_t smem, cudaStream_t st);
 
 struct ScanPlan {
-  int TQ, G, P, sortn, D_pad, nq_pad;
+  int TQ, TR, G, P, sortn, D_pad, nq_pad;      // TR: database rows per thread (2 only with TQ = 8, single-list kinds)
   int64_t rows_per_part;
   size_t smem;
   size_t off_qf, off_qn, off_partial, total_bytes;
@@ -108,21 +108,24 @@ inline ScanPlan make_scan_plan(int metric, int dtype, int64_t nq, int64_t N, int
   if (nl > 1 && nl * scan_sortn(k) * 8 * 8 > 100 * 1024) tq_max = 4;     // keep the lists of a CTA under ~100 KB
   (void)kind;
   pl.TQ = nq <= 1 ? 1 : (nq <= 4 ? 4 : tq_max);
+  // two rows per thread for the 8-query pass of the single-list kinds (a 256-row tile can add 256 candidates: 512-key lists)
+  pl.TR = (pl.TQ == 8 && nl == 1 && kind != K_MULTI && N >= 4 * kScanThreads) ? 2 : 1;
   pl.G = int(ceil_div64(nq, pl.TQ));
   pl.nq_pad = pl.G * pl.TQ;
   pl.D_pad = int(round_up64(D, DKE));
-  pl.sortn = pairwise ? 256 : scan_sortn(k);
-  pl.smem = size_t(kScanStages) * scan_stage_bytes(pl.TQ, DKE) + size_t(pl.TQ) * nl * pl.sortn * 8 + pl.TQ * nl * 16 + 64;
+  pl.sortn = pairwise ? 256 : (pl.TR == 2 ? 512 : scan_sortn(k));
+  pl.smem = size_t(kScanStages) * scan_stage_bytes(pl.TQ, DKE, pl.TR) + size_t(pl.TQ) * nl * pl.sortn * 8 + pl.TQ * nl * 16 + 64;
   int ctas_per_sm = int((227 * 1024) / (pl.smem + 1024));      // 1 KB per resident CTA is reserved by the driver
   ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
   const int64_t target = int64_t(kNumSMs) * ctas_per_sm;
   int64_t P = target / pl.G;
   if (P < 1) P = 1;
-  const int64_t ntiles = ceil_div64(N, kScanThreads);
+  const int tile_rows = kScanThreads * pl.TR;
+  const int64_t ntiles = ceil_div64(N, tile_rows);
   if (P > ntiles) P = ntiles;
   if (P < 1) P = 1;
-  pl.rows_per_part = round_up64(ceil_div64(N, P), kScanThreads);
-  if (pl.rows_per_part < kScanThreads) pl.rows_per_part = kScanThreads;
+  pl.rows_per_part = round_up64(ceil_div64(N, P), tile_rows);
+  if (pl.rows_per_part < tile_rows) pl.rows_per_part = tile_rows;
   pl.P = int(ceil_div64(N, pl.rows_per_part));
   if (pl.P < 1) pl.P = 1;
   size_t off = 0;

@@ -22,7 +22,7 @@ cudaError_t launch_prep_queries(int dtype, const void* Q, int nq, int D, int nq_
 // Tensor maps of the database shard (128-row x 128-byte boxes, 128-byte swizzle) and of the prepared fp32 queries
 // (TQ-row boxes).  Falls back to the cp.async loader (use_tma = 0) when rows are not 16-byte aligned or the driver
 // entry point is unavailable.
-static void setup_tma(ScanArgs& a, int dtype, int TQ, int nq_pad, size_t smem, CUtensorMap* tmX, CUtensorMap* tmQ) {
+static void setup_tma(ScanArgs& a, int dtype, int TQ, int nq_pad, size_t smem, CUtensorMap* tmX, CUtensorMap* tmQ, int TR = 1) {
   memset(tmX, 0, sizeof(*tmX));
   memset(tmQ, 0, sizeof(*tmQ));
   a.bar_off = int(smem) - 64;
@@ -30,7 +30,7 @@ static void setup_tma(ScanArgs& a, int dtype, int TQ, int nq_pad, size_t smem, C
   if (!a.aligned || a.N <= 0) return;
   const int esz = dtype == B200IR_F32 ? 4 : 2;
   const int DKE = kRowChunkBytes / esz;
-  if (!tma::encode_2d(tmX, esz, dtype == B200IR_BF16, a.X, a.N, a.D, int64_t(a.D) * esz, DKE, kScanThreads, true)) return;
+  if (!tma::encode_2d(tmX, esz, dtype == B200IR_BF16, a.X, a.N, a.D, int64_t(a.D) * esz, DKE, kScanThreads * TR, true)) return;
   if (!tma::encode_2d(tmQ, 4, false, a.Qf, nq_pad, a.D_pad, int64_t(a.D_pad) * 4, DKE, TQ, false)) return;
   a.use_tma = 1;
 }
@@ -73,8 +73,8 @@ cudaError_t run_scan(const ScanPlan& pl, int dtype, const void* Q, int64_t nq, c
     for (int m = 0; m < RK_COUNT; ++m) a.lslot[m] = (kind_mask >> m) & 1 ? (signed char)(a.nl++) : (signed char)-1;
   }
   CUtensorMap tmX, tmQ;
-  setup_tma(a, dtype, pl.TQ, pl.nq_pad, pl.smem, &tmX, &tmQ);
-  return dispatch_scan(kind, dtype == B200IR_F32, tmX, tmQ, a, pl.TQ, pl.smem, st);
+  setup_tma(a, dtype, pl.TQ, pl.nq_pad, pl.smem, &tmX, &tmQ, pl.TR);
+  return dispatch_scan(kind, dtype == B200IR_F32, tmX, tmQ, a, pl.TR == 2 ? 16 : pl.TQ, pl.smem, st);
 }
 
 FallbackPlan make_fallback_plan(int dtype, int64_t nq, int64_t N, int D, int k) {

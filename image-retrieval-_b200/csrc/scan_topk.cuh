@@ -86,13 +86,40 @@ __device__ __noinline__ void compact_candidates(uint64_t* keys, int* cnt, uint64
   __syncwarp();
 }
 
+// Two differences at once with ONE issue slot (sm_100 packed fp32: sub.rn.f32x2 -> SASS FADD2): the 8-query pass is
+// issue-bound (ncu: issue slots 73 % busy against 54 % for the FMA pipe), and the packed form keeps the arithmetic of
+// every element exactly as the scalar code has it.
+__device__ __forceinline__ void sub2(float x0, float x1, float q0, float q1, float& d0, float& d1) {
+  unsigned long long xa, qa, da;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(xa) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(qa) : "f"(q0), "f"(q1));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(da) : "l"(xa), "l"(qa));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(da));
+}
+__device__ __forceinline__ float fmax3_abs(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(fabsf(b)), "f"(fabsf(c)));     // 3-input max (sm_100)
+  return d;
+}
+
+// two consecutive elements of a row against two consecutive elements of a query
 template <int KIND>
-__device__ __forceinline__ void accum(float (&a)[(KIND == K_MULTI || KIND == K_EVAL || KIND == K_MULTI6) ? 4 : 1], float x, float q) {
-  if constexpr (KIND == K_L1) a[0] += fabsf(x - q);
-  else if constexpr (KIND == K_L2) { const float d = x - q; a[0] = fmaf(d, d, a[0]); }
-  else if constexpr (KIND == K_LINF) a[0] = fmaxf(a[0], fabsf(x - q));
-  else if constexpr (KIND == K_DOT) a[0] = fmaf(x, q, a[0]);
-  else { const float d = x - q; a[0] = fmaf(x, q, a[0]); a[1] += fabsf(d); a[2] = fmaf(d, d, a[2]); a[3] = fmaxf(a[3], fabsf(d)); }
+__device__ __forceinline__ void accum2(float (&a)[(KIND == K_MULTI || KIND == K_EVAL || KIND == K_MULTI6) ? 4 : 1], float x0, float x1,
+                                       float q0, float q1) {
+  if constexpr (KIND == K_DOT) { a[0] = fmaf(x0, q0, a[0]); a[0] = fmaf(x1, q1, a[0]); }
+  else {
+    float d0, d1;
+    sub2(x0, x1, q0, q1, d0, d1);
+    if constexpr (KIND == K_L1) { a[0] += fabsf(d0); a[0] += fabsf(d1); }
+    else if constexpr (KIND == K_L2) { a[0] = fmaf(d0, d0, a[0]); a[0] = fmaf(d1, d1, a[0]); }
+    else if constexpr (KIND == K_LINF) a[0] = fmax3_abs(a[0], d0, d1);
+    else {
+      a[0] = fmaf(x0, q0, a[0]); a[0] = fmaf(x1, q1, a[0]);
+      a[1] += fabsf(d0); a[1] += fabsf(d1);
+      a[2] = fmaf(d0, d0, a[2]); a[2] = fmaf(d1, d1, a[2]);
+      a[3] = fmax3_abs(a[3], d0, d1);
+    }
+  }
 }
 
 // rank value r (smaller = better) of one (query,row) pair from its accumulators
@@ -118,14 +145,18 @@ __device__ __forceinline__ float finish_rank(const float* acc, float xsq, float 
   }
 }
 
-template <int KIND, typename T, int TQ>
+// TR = database rows per thread (1, or 2 for the 8-query instantiations of the single-list kinds): with two rows per
+// thread every broadcast query load feeds two rows (half the LDS per FADD) and a thread carries 16 independent
+// accumulator chains, which is what the issue-bound 8-query pass and the batch regime (one pass per 8 queries) need.
+template <int KIND, typename T, int TQ, int TR = 1>
 __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                  const __grid_constant__ CUtensorMap tmQ, const ScanArgs a) {
   constexpr int DKE = kRowChunkBytes / int(sizeof(T));     // elements of a row per pipeline step
   constexpr int NA = (KIND == K_MULTI || KIND == K_EVAL || KIND == K_MULTI6) ? 4 : 1;
   constexpr bool NEED_XSQ = (KIND == K_DOT || KIND == K_MULTI || KIND == K_EVAL || KIND == K_MULTI6);
   const int NL = KIND == K_MULTI6 ? a.nl : 1;              // candidate lists per query
-  constexpr int XT_BYTES = kScanThreads * kRowChunkBytes;  // 16 KB database tile per stage
+  constexpr int TILE_ROWS = kScanThreads * TR;             // database rows per tile
+  constexpr int XT_BYTES = TILE_ROWS * kRowChunkBytes;     // 16 KB (32 KB) database tile per stage
   constexpr int QC_BYTES = TQ * DKE * 4;                   // fp32 query chunk per stage
   constexpr int STAGE_BYTES = XT_BYTES + (QC_BYTES + 1023) / 1024 * 1024;   // tiles stay 1024-byte aligned (TMA swizzle)
   constexpr int NST = KIND == K_EVAL ? kEvalStages : kScanStages;           // ring depth
@@ -177,7 +208,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
     for (int i = tid; i < nh; i += kScanThreads) ev_hist[i] = 0;
     for (int i = tid; i < a.nthr; i += kScanThreads) ev_thresholds[i] = a.thresholds[i];
   }
-  const int ntiles = int(ceil_div64(row_end - row_begin, kScanThreads));
+  const int ntiles = int(ceil_div64(row_end - row_begin, TILE_ROWS));
   const int nchunks = a.D_pad / DKE;
   const int total = ntiles * nchunks;
   const bool topk_mode = a.out_all == nullptr;
@@ -218,7 +249,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
           const uint32_t sbu = smem_u32(stage_base + iss_stage * STAGE_BYTES);
           const uint32_t bar = full_bar0 + 8u * iss_stage;
           tma::mbar_expect_tx(bar, XT_BYTES + QC_BYTES);
-          tma::load_2d(sbu, &tmX, bar, iss_chunk * DKE, int(row_begin + int64_t(iss_tile) * kScanThreads));
+          tma::load_2d(sbu, &tmX, bar, iss_chunk * DKE, int(row_begin + int64_t(iss_tile) * TILE_ROWS));
           tma::load_2d(sbu + XT_BYTES, &tmQ, bar, iss_chunk * DKE, g * TQ);
         }
         if (++iss_chunk == nchunks) { iss_chunk = 0; ++iss_tile; }
@@ -229,16 +260,16 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
     if (iss_tile < ntiles) {
       unsigned char* sb = stage_base + iss_stage * STAGE_BYTES;
       const uint32_t sbu = smem_u32(sb);
-      const int64_t row0 = row_begin + int64_t(iss_tile) * kScanThreads;
+      const int64_t row0 = row_begin + int64_t(iss_tile) * TILE_ROWS;
       const int64_t col_byte0 = int64_t(iss_chunk) * kRowChunkBytes;
-      const unsigned char* src0 = ld_src + int64_t(iss_tile) * (kScanThreads * row_bytes) + col_byte0;
-      const bool full = a.aligned && (row0 + kScanThreads <= row_end) && (col_byte0 + kRowChunkBytes <= row_bytes);
+      const unsigned char* src0 = ld_src + int64_t(iss_tile) * (TILE_ROWS * row_bytes) + col_byte0;
+      const bool full = a.aligned && (row0 + TILE_ROWS <= row_end) && (col_byte0 + kRowChunkBytes <= row_bytes);
       if (full) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cp_async_16(sbu + ld_dst + i * 2048, src0 + i * ld_istride, 16);
+        for (int i = 0; i < 8 * TR; ++i) cp_async_16(sbu + ld_dst + i * 2048, src0 + i * ld_istride, 16);
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 8 * TR; ++i) {
           const int64_t grow = row0 + ld_r0 + 16 * i;
           const int64_t cb = col_byte0 + ld_c * 16;
           int nbytes = 0;
@@ -268,12 +299,16 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
 #pragma unroll
   for (int s = 0; s < NST - 1; ++s) issue();
 
-  float acc[TQ][NA];
-  float xsq = 0.f;
+  float acc[TR][TQ][NA];
+  float xsq[TR];
 #pragma unroll
-  for (int t = 0; t < TQ; ++t)
+  for (int r = 0; r < TR; ++r) {
+    xsq[r] = 0.f;
 #pragma unroll
-    for (int j = 0; j < NA; ++j) acc[t][j] = 0.f;
+    for (int t = 0; t < TQ; ++t)
+#pragma unroll
+      for (int j = 0; j < NA; ++j) acc[r][t][j] = 0.f;
+  }
 
   float qn[TQ];
 #pragma unroll
@@ -299,60 +334,86 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
 
     const unsigned char* sb = stage_base + stage * STAGE_BYTES;
     if (++stage == NST) stage = 0;
-    const unsigned char* xrow = sb + tid * kRowChunkBytes;
+    const unsigned char* xrow = sb + tid * kRowChunkBytes;                 // row r of this thread: tile row tid + 128 r
     const float* qs = reinterpret_cast<const float*>(sb + XT_BYTES);
 
-    float part[TQ][NA];
-    float xpart = 0.f;
+    float part[TR][TQ][NA];
+    float xpart[TR];
 #pragma unroll
-    for (int t = 0; t < TQ; ++t)
+    for (int r = 0; r < TR; ++r) {
+      xpart[r] = 0.f;
 #pragma unroll
-      for (int j = 0; j < NA; ++j) part[t][j] = (KIND == K_LINF || j == 3) ? acc[t][j] : 0.f;
+      for (int t = 0; t < TQ; ++t)
+#pragma unroll
+        for (int j = 0; j < NA; ++j) part[r][t][j] = (KIND == K_LINF || j == 3) ? acc[r][t][j] : 0.f;
+    }
 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(xrow + ((j ^ (tid & 7)) << 4));
-      if constexpr (sizeof(T) == 4) {
-        const float x[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
-        if constexpr (NEED_XSQ) {
+      uint4 raw[TR];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) xpart = fmaf(x[e], x[e], xpart);
+      for (int r = 0; r < TR; ++r)
+        raw[r] = *reinterpret_cast<const uint4*>(xrow + r * (kScanThreads * kRowChunkBytes) + ((j ^ (tid & 7)) << 4));
+      if constexpr (sizeof(T) == 4) {
+        float x[TR][4];
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          x[r][0] = __uint_as_float(raw[r].x); x[r][1] = __uint_as_float(raw[r].y);
+          x[r][2] = __uint_as_float(raw[r].z); x[r][3] = __uint_as_float(raw[r].w);
+          if constexpr (NEED_XSQ) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xpart[r] = fmaf(x[r][e], x[r][e], xpart[r]);
+          }
         }
 #pragma unroll
         for (int t = 0; t < TQ; ++t) {
           const float4 q4 = *reinterpret_cast<const float4*>(qs + t * DKE + j * 4);
-          accum<KIND>(part[t], x[0], q4.x); accum<KIND>(part[t], x[1], q4.y);
-          accum<KIND>(part[t], x[2], q4.z); accum<KIND>(part[t], x[3], q4.w);
+#pragma unroll
+          for (int r = 0; r < TR; ++r) {
+            accum2<KIND>(part[r][t], x[r][0], x[r][1], q4.x, q4.y);
+            accum2<KIND>(part[r][t], x[r][2], x[r][3], q4.z, q4.w);
+          }
         }
       } else {
-        const float x[8] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y),
-                            bf16_lo(raw.z), bf16_hi(raw.z), bf16_lo(raw.w), bf16_hi(raw.w)};
-        if constexpr (NEED_XSQ) {
+        float x[TR][8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) xpart = fmaf(x[e], x[e], xpart);
+        for (int r = 0; r < TR; ++r) {
+          x[r][0] = bf16_lo(raw[r].x); x[r][1] = bf16_hi(raw[r].x); x[r][2] = bf16_lo(raw[r].y); x[r][3] = bf16_hi(raw[r].y);
+          x[r][4] = bf16_lo(raw[r].z); x[r][5] = bf16_hi(raw[r].z); x[r][6] = bf16_lo(raw[r].w); x[r][7] = bf16_hi(raw[r].w);
+          if constexpr (NEED_XSQ) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xpart[r] = fmaf(x[r][e], x[r][e], xpart[r]);
+          }
         }
 #pragma unroll
         for (int t = 0; t < TQ; ++t) {
           const float4 qa = *reinterpret_cast<const float4*>(qs + t * DKE + j * 8);
           const float4 qb = *reinterpret_cast<const float4*>(qs + t * DKE + j * 8 + 4);
-          accum<KIND>(part[t], x[0], qa.x); accum<KIND>(part[t], x[1], qa.y);
-          accum<KIND>(part[t], x[2], qa.z); accum<KIND>(part[t], x[3], qa.w);
-          accum<KIND>(part[t], x[4], qb.x); accum<KIND>(part[t], x[5], qb.y);
-          accum<KIND>(part[t], x[6], qb.z); accum<KIND>(part[t], x[7], qb.w);
+#pragma unroll
+          for (int r = 0; r < TR; ++r) {
+            accum2<KIND>(part[r][t], x[r][0], x[r][1], qa.x, qa.y);
+            accum2<KIND>(part[r][t], x[r][2], x[r][3], qa.z, qa.w);
+            accum2<KIND>(part[r][t], x[r][4], x[r][5], qb.x, qb.y);
+            accum2<KIND>(part[r][t], x[r][6], x[r][7], qb.z, qb.w);
+          }
         }
       }
     }
     // two-level summation: chunk partial -> row total (keeps fp32 error ~ sqrt-free (DKE + D/DKE) eps)
 #pragma unroll
-    for (int t = 0; t < TQ; ++t)
+    for (int r = 0; r < TR; ++r) {
 #pragma unroll
-      for (int j = 0; j < NA; ++j) acc[t][j] = (KIND == K_LINF || j == 3) ? part[t][j] : acc[t][j] + part[t][j];
-    xsq += xpart;
+      for (int t = 0; t < TQ; ++t)
+#pragma unroll
+        for (int j = 0; j < NA; ++j) acc[r][t][j] = (KIND == K_LINF || j == 3) ? part[r][t][j] : acc[r][t][j] + part[r][t][j];
+      xsq[r] += xpart[r];
+    }
 
     if (++chunk == nchunks) {
       chunk = 0;
-      const int64_t grow = row_begin + int64_t(tile) * kScanThreads + tid;
-      ++tile;
+#pragma unroll
+      for (int r = 0; r < TR; ++r) {
+      const int64_t grow = row_begin + int64_t(tile) * TILE_ROWS + r * kScanThreads + tid;
       const bool valid = grow < row_end;
 #pragma unroll
       for (int t = 0; t < TQ; ++t) {
@@ -360,11 +421,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
         if constexpr (KIND == K_EVAL) {
           if (valid && q < nq_eff && grow > q) {
             // the five evaluation metrics of mi_analysis.py:183-189 from one pass (geometric_metrics.py:114-129)
-            const float xn = sqrtf(xsq);
+            const float xn = sqrtf(xsq[r]);
             float cs = 0.f;
-            if (qn[t] != 0.f && xn != 0.f) cs = acc[t][0] / (qn[t] * xn);
+            if (qn[t] != 0.f && xn != 0.f) cs = acc[r][t][0] / (qn[t] * xn);
             const float fD = float(a.mp.D);
-            const float vals[kEvalMetrics] = {1.0f - cs, acc[t][1] / fD, sqrtf(acc[t][2]) / sqrtf(fD), acc[t][3], fabsf(qn[t] - xn)};
+            const float vals[kEvalMetrics] = {1.0f - cs, acc[r][t][1] / fD, sqrtf(acc[r][t][2]) / sqrtf(fD), acc[r][t][3], fabsf(qn[t] - xn)};
             const int rel = (a.cat[q] == a.cat[grow] ? 0 : 2) + (a.col[q] == a.col[grow] ? 0 : 1);   // mi_analysis.py:176-181
 #pragma unroll
             for (int m = 0; m < kEvalMetrics; ++m) {
@@ -388,15 +449,15 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
         if (valid && q < nq_eff) {
           if constexpr (KIND == K_MULTI6) {
             // all six rankings of this (query, row) pair from the four accumulators (geometric_metrics.py:12-57, :85-92)
-            const float xn = sqrtf(xsq);
+            const float xn = sqrtf(xsq[r]);
             float cs = 0.f;
-            if (qn[t] != 0.f && xn != 0.f) cs = acc[t][0] / (qn[t] * xn);
+            if (qn[t] != 0.f && xn != 0.f) cs = acc[r][t][0] / (qn[t] * xn);
             const float fD = float(a.mp.D);
             const float mag = fabsf(qn[t] - xn);
-            float sim = a.mp.w[0] * cs - a.mp.w[1] * (acc[t][1] / fD) - a.mp.w[2] * (sqrtf(acc[t][2]) / sqrtf(fD)) - a.mp.w[3] * acc[t][3] -
+            float sim = a.mp.w[0] * cs - a.mp.w[1] * (acc[r][t][1] / fD) - a.mp.w[2] * (sqrtf(acc[r][t][2]) / sqrtf(fD)) - a.mp.w[3] * acc[r][t][3] -
                         a.mp.w[4] * mag;
             if (a.mp.flags & B200IR_FLAG_ABS_SCORE) { cs = fabsf(cs); sim = fabsf(sim); }
-            const float rk[RK_COUNT] = {-cs, acc[t][1], acc[t][2], acc[t][3], mag, -sim};
+            const float rk[RK_COUNT] = {-cs, acc[r][t][1], acc[r][t][2], acc[r][t][3], mag, -sim};
 #pragma unroll
             for (int m = 0; m < RK_COUNT; ++m) {
               const int ls = a.lslot[m];
@@ -410,29 +471,31 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
               }
             }
           } else {
-          const float r = finish_rank<KIND>(acc[t], xsq, qn[t], a.mp);
+          const float rv = finish_rank<KIND>(acc[r][t], xsq[r], qn[t], a.mp);
           if (topk_mode) {
-            const uint64_t key = make_key(r, uint32_t(grow));
+            const uint64_t key = make_key(rv, uint32_t(grow));
             if (key < thr_s[t] && (!paged || key > a.after[g * TQ + t])) {     // cursor read only on the (rare) hit path
               const int slot = atomicAdd(&cnt_s[t], 1);
               keys_s[size_t(t) * a.sortn + slot] = key;
             }
           } else {
-            a.out_all[int64_t(q) * a.N + grow] = rank_to_score(r, a.mp.metric, a.mp.flags, a.mp.D);
+            a.out_all[int64_t(q) * a.N + grow] = rank_to_score(rv, a.mp.metric, a.mp.flags, a.mp.D);
           }
           }
         }
 #pragma unroll
-        for (int j = 0; j < NA; ++j) acc[t][j] = 0.f;
+        for (int j = 0; j < NA; ++j) acc[r][t][j] = 0.f;
       }
-      xsq = 0.f;
+      xsq[r] = 0.f;
+      }
+      ++tile;
       if constexpr (KIND == K_EVAL) {
         if (tile % kEvalFlushTiles == 0) flush_bins();
       }
       if (KIND != K_EVAL && topk_mode) {
         __syncthreads();
         for (int t = warp; t < TQ * NL; t += kScanThreads / 32) {
-          if (cnt_s[t] > a.sortn - kScanThreads) {
+          if (cnt_s[t] > a.sortn - TILE_ROWS) {
             if (a.sortn == 256) compact_candidates<8>(keys_s + size_t(t) * a.sortn, &cnt_s[t], &thr_s[t], a.k, lane);
             else compact_candidates<16>(keys_s + size_t(t) * a.sortn, &cnt_s[t], &thr_s[t], a.k, lane);
           }
@@ -466,9 +529,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
 }
 
 
-template <int KIND, typename T, int TQ>
+template <int KIND, typename T, int TQ, int TR = 1>
 inline cudaError_t launch_scan_inst(const CUtensorMap& tmX, const CUtensorMap& tmQ, const ScanArgs& a, size_t smem, cudaStream_t st) {
-  auto kern = scan_topk_kernel<KIND, T, TQ>;
+  auto kern = scan_topk_kernel<KIND, T, TQ, TR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   kern<<<a.G * a.P, kScanThreads, smem, st>>>(tmX, tmQ, a);
@@ -485,6 +548,9 @@ inline cudaError_t launch_scan_tq(const CUtensorMap& tmX, const CUtensorMap& tmQ
     case 1: return launch_scan_inst<KIND, T, 1>(tmX, tmQ, a, smem, st);
     case 4: return launch_scan_inst<KIND, T, 4>(tmX, tmQ, a, smem, st);
     case 8: return launch_scan_inst<KIND, T, 8>(tmX, tmQ, a, smem, st);
+    case 16:                                              // TQ code 16 = 8 queries x 2 rows per thread (single-list kinds)
+      if constexpr (KIND == K_L1 || KIND == K_L2 || KIND == K_LINF || KIND == K_DOT) return launch_scan_inst<KIND, T, 8, 2>(tmX, tmQ, a, smem, st);
+      else return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
 }

@@ -150,8 +150,10 @@ def test_topk_edge_cases(ops):
     assert np.all(full[:, 2] == 0)
     with pytest.raises(ValueError):
         ops.topk(Q, X, "l1", 0)
+    s, i = ops.topk(Q, X, "l1", 257)                       # more than one 256-row page: served page by page, padded past N
+    assert s.shape == (3, 257) and np.all(i[:, 5:].cpu().numpy() == -1)
     with pytest.raises(ValueError):
-        ops.topk(Q, X, "l1", 257)
+        ops.topk(Q, X, "l1", 4097)
     with pytest.raises(ValueError):
         ops.topk(Q, synth.gaussian(5, 17, 3), "l1", 2)
     # unaligned view (row stride not a multiple of 16 bytes is copied to contiguous by as_device_matrix)
