@@ -55,6 +55,9 @@ _SIGNATURES = {
     "b200ir_allpairs_eval": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
                                               ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double), ctypes.c_int,
                                               c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "b200ir_allpairs_eval_part": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
+                                                   ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double), ctypes.c_int,
+                                                   ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "b200ir_pair_metrics": (ctypes.c_int, [ctypes.c_int, c_vp, c_i64, c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "b200ir_threshold_dedupe": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_i64, ctypes.c_double, ctypes.c_int,
                                                ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),

@@ -421,6 +421,14 @@ size_t b200ir_allpairs_eval_workspace_bytes(int64_t N, int D, int nthr) {
 int b200ir_allpairs_eval(const float* X, const int32_t* cat, const int32_t* col, int64_t N, int D, int nbins,
                          const float* lo_host, const float* hi_host, const double* thresholds_host, int nthr,
                          uint64_t* hist, uint64_t* thr_counts, void* workspace, size_t workspace_bytes, void* stream) {
+  return b200ir_allpairs_eval_part(X, cat, col, N, D, nbins, lo_host, hi_host, thresholds_host, nthr, 0, 1, hist, thr_counts, workspace,
+                                   workspace_bytes, stream);
+}
+
+int b200ir_allpairs_eval_part(const float* X, const int32_t* cat, const int32_t* col, int64_t N, int D, int nbins,
+                              const float* lo_host, const float* hi_host, const double* thresholds_host, int nthr, int part, int nparts,
+                              uint64_t* hist, uint64_t* thr_counts, void* workspace, size_t workspace_bytes, void* stream) {
+  if (nparts < 1 || part < 0 || part >= nparts) return B200IR_E_ARG;
   if (N < 0 || D <= 0 || nbins < 1 || nbins > 1024 || nthr < 0 || nthr > 1024) return B200IR_E_ARG;
   if (N >= (int64_t(1) << 31)) return B200IR_E_SHAPE;
   if (!hist || !thr_counts || !lo_host || !hi_host || (nthr > 0 && !thresholds_host)) return B200IR_E_ARG;
@@ -438,7 +446,7 @@ int b200ir_allpairs_eval(const float* X, const int32_t* cat, const int32_t* col,
   if (reinterpret_cast<uintptr_t>(workspace) % 256) return B200IR_E_ALIGN;
   return int(run_allpairs_eval(X, cat, col, N, D, nbins, lo_host, hi_host, thresholds_host, nthr,
                                reinterpret_cast<unsigned long long*>(hist), reinterpret_cast<unsigned long long*>(thr_counts),
-                               static_cast<unsigned char*>(workspace), st));
+                               static_cast<unsigned char*>(workspace), st, part, nparts));
 }
 
 int b200ir_pair_metrics(int dtype, const void* A, int64_t NA, const void* B, int64_t NB, int D,

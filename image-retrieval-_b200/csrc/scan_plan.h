@@ -59,6 +59,8 @@ struct ScanArgs {
   // [gate_base, gate_base + nq) of a device-side list whose length *gate is only known on the device
   const int* gate;        // nullptr: plain launch
   int gate_base;
+  // evaluation mode across GPUs: this launch serves query groups g_first, g_first + g_stride, ... (g_stride 0 == 1)
+  int g_first, g_stride;
   // paging (result pages beyond B200IR_MAX_K): only keys strictly after the cursor of the previous page are candidates
   const uint64_t* after;  // [nq] or nullptr
   // K_MULTI6: list slot of each ranking kind (-1: not requested) and the number of lists kept per query
@@ -172,6 +174,7 @@ cudaError_t run_scan(const ScanPlan& pl, int dtype, const void* Q, int64_t nq, c
 size_t allpairs_eval_workspace_bytes(int64_t N, int D, int nthr);
 cudaError_t run_allpairs_eval(const float* X, const int32_t* cat, const int32_t* col, int64_t N, int D, int nbins,
                               const float* lo, const float* hi, const double* thresholds_host, int nthr,
-                              unsigned long long* hist, unsigned long long* thr_counts, unsigned char* ws, cudaStream_t st);
+                              unsigned long long* hist, unsigned long long* thr_counts, unsigned char* ws, cudaStream_t st,
+                              int part = 0, int nparts = 1);
 
 }  // namespace b200ir

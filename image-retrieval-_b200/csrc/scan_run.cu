@@ -160,7 +160,8 @@ size_t allpairs_eval_workspace_bytes(int64_t N, int D, int nthr) {
 
 cudaError_t run_allpairs_eval(const float* X, const int32_t* cat, const int32_t* col, int64_t N, int D, int nbins,
                               const float* lo, const float* hi, const double* thresholds_host, int nthr,
-                              unsigned long long* hist, unsigned long long* thr_counts, unsigned char* ws, cudaStream_t st) {
+                              unsigned long long* hist, unsigned long long* thr_counts, unsigned char* ws, cudaStream_t st,
+                              int part, int nparts) {
   const int D_pad = int(round_up64(D, 32));
   const int64_t n_pad = round_up64(N, kEvalTQ);
   size_t off = 0;
@@ -177,7 +178,12 @@ cudaError_t run_allpairs_eval(const float* X, const int32_t* cat, const int32_t*
   if (e != cudaSuccess) return e;
   ScanArgs a{};
   a.X = X; a.N = N; a.D = D; a.Qf = Qf; a.qnorm = qn; a.nq = int(N); a.D_pad = D_pad;
-  a.G = int(n_pad / kEvalTQ); a.P = 1; a.rows_per_part = round_up64(N, kScanThreads); a.k = 1; a.sortn = 256;
+  // query groups are dealt to the parts cyclically (the pair grid is triangular: low groups meet the most rows)
+  const int groups = int(n_pad / kEvalTQ);
+  a.g_first = part; a.g_stride = nparts;
+  a.G = part < groups ? (groups - part + nparts - 1) / nparts : 0;
+  a.P = 1; a.rows_per_part = round_up64(N, kScanThreads); a.k = 1; a.sortn = 256;
+  if (a.G == 0) return cudaSuccess;
   a.aligned = ((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (int64_t(D) * 4) % 16 == 0) ? 1 : 0;
   a.partial = nullptr;
   a.out_all = nullptr;

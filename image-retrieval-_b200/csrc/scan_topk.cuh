@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const __grid_co
   int* cnt_s = reinterpret_cast<int*>(thr_s + TQ * NL);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = blockIdx.x % a.G;
+  const int g = a.g_first + (blockIdx.x % a.G) * (a.g_stride > 0 ? a.g_stride : 1);
   const int p = blockIdx.x / a.G;
   int nq_eff = a.nq;
   if (a.gate != nullptr) {                                 // fallback tier: serve only the list positions that exist

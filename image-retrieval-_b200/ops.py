@@ -370,9 +370,10 @@ EVAL_METRICS = ("cosine_distance", "l1_distance", "l2_distance", "linf_distance"
 RELATIONSHIP_TYPES = ("same_object_same_color", "same_object_diff_color", "diff_object_same_color", "diff_object_diff_color")
 
 
-def allpairs_eval(X, category, color, ranges, nbins=1024, thresholds=None):
+def allpairs_eval(X, category, color, ranges, nbins=1024, thresholds=None, part=0, nparts=1):
     """All-pairs evaluation counts (mi_analysis.py:256-297, :704-713, :774-796) over every pair i < j.
-    Returns (hist (5, 4, nbins) int64, thr_counts (5, 2, nthr + 1) int64) device tensors; see include/b200ir.h."""
+    Returns (hist (5, 4, nbins) int64, thr_counts (5, 2, nthr + 1) int64) device tensors; see include/b200ir.h.
+    part / nparts: only this part's cyclic share of the rows i (the parts' counts add up; sharded.allpairs_eval)."""
     X = as_device_matrix(X, dtype=torch.float32)
     N, D = X.shape
     cat = torch.as_tensor(category, dtype=torch.int32).to(X.device).contiguous()
@@ -389,8 +390,8 @@ def allpairs_eval(X, category, color, ranges, nbins=1024, thresholds=None):
     lib = _lib.load()
     need = lib.b200ir_allpairs_eval_workspace_bytes(N, D, nthr)
     ws = _workspace(need, X.device)
-    st = lib.b200ir_allpairs_eval(_ptr(X), _ptr(cat), _ptr(col), N, D, nbins, lo, hi, thr, nthr, _ptr(hist), _ptr(thr_counts),
-                                  _ptr(ws), ws.numel(), _stream())
+    st = lib.b200ir_allpairs_eval_part(_ptr(X), _ptr(cat), _ptr(col), N, D, nbins, lo, hi, thr, nthr, int(part), int(nparts), _ptr(hist),
+                                       _ptr(thr_counts), _ptr(ws), ws.numel(), _stream())
     _lib.check(st, "allpairs_eval")
     torch.cuda.current_stream().synchronize()          # thresholds are read from host memory by an async copy
     return hist, thr_counts

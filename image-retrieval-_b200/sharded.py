@@ -121,3 +121,19 @@ class ShardedIndex:
         dist.all_gather_into_tensor(out_s, ms.contiguous(), group=self.group)
         dist.all_gather_into_tensor(out_i, mi.contiguous(), group=self.group)
         return out_s[:nq], out_i[:nq]
+
+
+def allpairs_eval(X, category, color, ranges, nbins=1024, thresholds=None, group=None, local_eval=None):
+    """BASELINE configs[4] across GPUs: the store is replicated, rank r counts the pairs (i, j > i)
+    of its cyclic share of the rows i, and ONE all-reduce of the integer count tensors gives every rank the totals.
+    `local_eval(part, nparts) -> (hist, thr_counts)` is injectable for the gloo test; default: ops.allpairs_eval."""
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    R, r = (dist.get_world_size(group), dist.get_rank(group)) if multi else (1, 0)
+    if local_eval is None:
+        hist, thr = ops.allpairs_eval(X, category, color, ranges, nbins, thresholds, part=r, nparts=R)
+    else:
+        hist, thr = local_eval(r, R)
+    if multi:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(thr, op=dist.ReduceOp.SUM, group=group)
+    return hist, thr

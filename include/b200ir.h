@@ -215,6 +215,13 @@ int b200ir_allpairs_eval(const float* X, const int32_t* cat, const int32_t* col,
                          const float* lo_host, const float* hi_host, const double* thresholds_host, int nthr,
                          uint64_t* hist, uint64_t* thr_counts, void* workspace, size_t workspace_bytes, void* stream);
 
+/* One part of the same evaluation for a store replicated on `nparts` GPUs: part `part` counts the pairs (i, j > i) of
+ * its cyclic share of the rows i (groups of 8 rows dealt round-robin: the pair grid is triangular).  The parts' hist /
+ * thr_counts add up to b200ir_allpairs_eval's (one all-reduce of the integer count tensors). */
+int b200ir_allpairs_eval_part(const float* X, const int32_t* cat, const int32_t* col, int64_t N, int D, int nbins,
+                              const float* lo_host, const float* hi_host, const double* thresholds_host, int nthr, int part, int nparts,
+                              uint64_t* hist, uint64_t* thr_counts, void* workspace, size_t workspace_bytes, void* stream);
+
 /*
  * Explicit pair lists: replaces the per-pair get_all_metrics calls of ColorMIAnalyzer.calculate_distances
  * (mi_analysis.py:256-297 over pairs.json; geometric_metrics.py:114-129).  For p in [0, P): the pair

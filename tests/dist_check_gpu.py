@@ -36,6 +36,17 @@ def main():
         ok = ok and same
         if rank == 0:
             print(f"{metric:18s} {str(dtype):15s} k={k:3d} sharded==single: {same}")
+    # all-pairs evaluation (config 5) across GPUs: replicated store, cyclic row shares, one all-reduce of the counts
+    from image_retrieval_b200 import sharded
+    Xe = X[:4000, :64].contiguous()
+    cat, col = (torch.arange(4000) % 10).numpy(), ((torch.arange(4000) // 10) % 3).numpy()
+    ranges = {m: (0.0, 4.0) for m in ops.EVAL_METRICS}
+    h1, t1 = ops.allpairs_eval(Xe, cat, col, ranges, 256)
+    h2, t2 = sharded.allpairs_eval(Xe, cat, col, ranges, 256)
+    same = torch.equal(h1, h2) and torch.equal(t1, t2)
+    ok = ok and same
+    if rank == 0:
+        print(f"allpairs_eval sharded==single: {same}")
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()

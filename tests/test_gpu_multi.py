@@ -205,3 +205,23 @@ def test_path_groups_follow_collection_changes(ops):
     assert [r["path"] for r in res].count("p3") == 1
     s.collection = ([f"q{i}" for i in range(30)], X)                # tuple collection of the same length: no stale groups
     assert s._path_groups(s._store()[0]) is None
+
+
+def test_allpairs_eval_parts_add_up(ops):
+    """The cyclic row shares of b200ir_allpairs_eval_part (what each GPU of a replicated store counts) sum to the
+    unsharded evaluation exactly - integer counts, so the all-reduce across GPUs is exact too."""
+    import torch
+    N = 1000
+    X = synth.gaussian(N, 64, 151)
+    cat, col = np.arange(N) % 7, (np.arange(N) // 7) % 3
+    ranges = {"cosine_distance": (0.0, 2.0), "l1_distance": (0.0, 2.5), "l2_distance": (0.0, 3.0), "linf_distance": (0.0, 8.0),
+              "magnitude_difference": (0.0, 5.0)}
+    h, t = ops.allpairs_eval(X, cat, col, ranges, 128)
+    for nparts in (2, 3, 8):
+        hs, ts = torch.zeros_like(h), torch.zeros_like(t)
+        for part in range(nparts):
+            hp, tp = ops.allpairs_eval(X, cat, col, ranges, 128, part=part, nparts=nparts)
+            hs += hp
+            ts += tp
+        assert torch.equal(hs, h) and torch.equal(ts, t), nparts
+    assert int(h[0].sum()) == N * (N - 1) // 2

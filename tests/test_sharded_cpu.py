@@ -81,3 +81,49 @@ def test_sharded_search_equals_single(tmp_path, world):
             assert np.array_equal(r[f"{metric}_i"], i), metric
             assert np.array_equal(r[f"{metric}_s"], v.astype(np.float32)), metric
     assert list(ranks[0]["l1_i"][0, :2]) == [3, 900]
+
+
+def _eval_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from image_retrieval_b200 import sharded
+    from oracle import evaluation as E
+    from oracle import synth
+    N, nbins = 203, 64
+    X = synth.gaussian(N, 24, 17)
+    cat, col = np.arange(N) % 5, (np.arange(N) // 5) % 3
+    ranges = {m: (0.0, 4.0) for m in E.METRICS}
+    thresholds = np.linspace(0, 1, 20)
+    vals = E.metric_matrices(X, np.float32)
+
+    def local_eval(part, nparts):
+        # this part's rows i: groups of 8 rows dealt round-robin (what b200ir_allpairs_eval_part counts)
+        rel = E.relationship(cat, col).copy()
+        mine = (np.arange(N) // 8) % nparts == part
+        rel[~mine, :] = 9                                   # pairs (i, j > i) of foreign rows i match no relationship type
+        h, t = E.bin_counts(vals, rel, ranges, nbins, thresholds)
+        return torch.from_numpy(h), torch.from_numpy(t)
+
+    hist, thr = sharded.allpairs_eval(X, cat, col, ranges, nbins, thresholds, local_eval=local_eval)
+    np.savez(os.path.join(out_dir, f"eval{rank}.npz"), hist=hist.numpy(), thr=thr.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_sharded_allpairs_eval_counts_add_up(tmp_path):
+    """3 gloo ranks: the cyclic row shares + one all-reduce of the integer counts equal the unsharded evaluation."""
+    from oracle import evaluation as E
+    from oracle import synth
+    world = 3
+    mp.spawn(_eval_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    N, nbins = 203, 64
+    X = synth.gaussian(N, 24, 17)
+    cat, col = np.arange(N) % 5, (np.arange(N) // 5) % 3
+    ranges = {m: (0.0, 4.0) for m in E.METRICS}
+    h, t = E.bin_counts(E.metric_matrices(X, np.float32), E.relationship(cat, col), ranges, nbins, np.linspace(0, 1, 20))
+    for r in range(world):
+        got = np.load(tmp_path / f"eval{r}.npz")
+        assert np.array_equal(got["hist"], h) and np.array_equal(got["thr"], t)
