@@ -39,7 +39,8 @@ constexpr int BM = 128;            // queries per tile (UMMA M, TMEM lanes)
 constexpr int BN = GEMM_BN;        // database rows per tile (UMMA N, TMEM columns per accumulator)
 constexpr int BK = 64;             // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int MAX_KB = 8;          // D <= 512
+constexpr int MAX_KB = 8;          // D <= 512: the query tile stays resident in shared memory
+constexpr int MAX_D_STREAM = 2048; // beyond 512 the query k-blocks are streamed (A-streamed kernel variant)
 constexpr int TMEM_COLS = 512;
 constexpr int NBUF = TMEM_COLS / BN;         // accumulators in flight (2 x 256 or 4 x 128 columns)
 constexpr int B_STAGES = BN == 256 ? 3 : 5;
@@ -51,6 +52,10 @@ constexpr int SMEM_SCALE = NBUF * BN * 4;    // per-column scale (rnorm / sqnorm
 constexpr int SMEM_BARS = BN == 256 ? 192 : 320;
 constexpr int SMEM_CNT = 3 * BM * 2;        // per-query 16-bit counters: front (warp 0 of the quarter), back (warp 1), sorted prefix
 constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS + SMEM_CNT;   // 232,384 B <= 232,448
+// A-streamed variant (D > 512: the query tile no longer fits next to the ring): no resident A, a 13-slot ring of 16 KB
+constexpr int STREAM_SLOTS = 13;
+constexpr int SMEM_BARS_STREAM = 320;
+constexpr int SMEM_TOTAL_STREAM = STREAM_SLOTS * (B_STAGE_BYTES / 2) + SMEM_SCALE + SMEM_BARS_STREAM + SMEM_CNT;
 constexpr int THREADS = 384;           // 4 control warps + 8 epilogue warps (two per TMEM lane quarter)
 static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 
@@ -374,25 +379,35 @@ __device__ __forceinline__ float score_of(float dot, float s) {
 //         accumulator.  q_hi is the resident A operand; x_hi, x_lo and this CTA's q_lo k-block take one ring slot
 //         each (the same 16 KB), so a k-block costs three slots and twelve MMAs and the bytes staged per MMA are the
 //         same as in the bf16 kernel.  tmA2 / tmB2 are the tensor maps of the lo planes (NT = 1: unused copies).
-template <int MODE, int NCTA, int NT>
+// ARES = true:  D <= 512, the query tile (q / q_hi) is resident in shared memory for the whole unit (above).
+// ARES = false: any D (host limit 2048): nothing is resident, the query k-blocks ride the ring next to the database
+//         k-blocks (bf16: x, q = 2 slots per k-block; fp32: x_hi, q_hi, x_lo, q_lo = 4 slots).  Twice the L2 -> SM bytes
+//         per FLOP, so this variant is L2-bandwidth bound well below the resident kernel - and still tens of times
+//         faster than the CUDA-core scan those shapes used to fall back to.
+template <int MODE, int NCTA, int NT, bool ARES>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2, const Args a) {
   static_assert(NT == 1 || (NT == 3 && NCTA == 2), "the split mode is built for the CTA-pair kernel only");
+  static_assert(ARES || NCTA == 2, "the A-streamed variant is built for the CTA-pair kernel only");
   // NCTA == 2: the CTA pair of a cluster works on two query tiles and shares every database tile: each CTA stages
   // HALF of the tile's rows (16 KB per k-block instead of 32 KB, so the ring is 6 deep), the leader issues
   // tcgen05.mma.cta_group::2 (M = 256 across the pair) and each SM's tensor core reads both halves: shared-memory
   // traffic per FLOP drops by a third, which is what bounds the 1-CTA kernel.
-  constexpr int NST = NCTA == 2 ? 2 * B_STAGES : B_STAGES;          // ring depth
+  constexpr int NST = !ARES ? STREAM_SLOTS : (NCTA == 2 ? 2 * B_STAGES : B_STAGES);          // ring depth
   constexpr int STAGE_BYTES = B_STAGE_BYTES / NCTA;                  // bytes of one k-block staged per CTA
   constexpr int BN_CTA = BN / NCTA;                                  // database rows staged per CTA
+  constexpr int A_BYTES = ARES ? SMEM_A : 0;
+  constexpr int RING_BYTES = NST * STAGE_BYTES;
+  constexpr int BARS_BYTES = ARES ? SMEM_BARS : SMEM_BARS_STREAM;
+  constexpr int SLOTS = ARES ? NT : (NT == 1 ? 2 : 4);               // ring slots per k-block
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
-  uint8_t* sB = smem + SMEM_A;
-  float* sScale = reinterpret_cast<float*>(smem + SMEM_A + SMEM_B);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_A + SMEM_B + SMEM_SCALE);
+  uint8_t* sB = smem + A_BYTES;
+  float* sScale = reinterpret_cast<float*>(smem + A_BYTES + RING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + RING_BYTES + SMEM_SCALE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 2 + 4 * NBUF);
-  unsigned short* cnt_s = reinterpret_cast<unsigned short*>(smem + SMEM_A + SMEM_B + SMEM_SCALE + SMEM_BARS);
+  unsigned short* cnt_s = reinterpret_cast<unsigned short*>(smem + A_BYTES + RING_BYTES + SMEM_SCALE + BARS_BYTES);
 
   const uint32_t bar0 = smem_u32(bars);
   auto B_FULL = [&](int s) { return bar0 + 8u * s; };
@@ -402,7 +417,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto T_EMPTY = [&](int b) { return bar0 + 8u * (2 * NST + 2 + NBUF + b); };     // local: this CTA's epilogue released buffer b
   auto S_FULL = [&](int b) { return bar0 + 8u * (2 * NST + 2 + 2 * NBUF + b); };
   auto TE_MMA = [&](int b) { return bar0 + 8u * (2 * NST + 2 + 3 * NBUF + b); };  // leader: every epilogue warp of the cluster released b
-  static_assert((2 * NST + 2 + 4 * NBUF) * 8 + 8 <= SMEM_BARS, "barrier area");
+  static_assert((2 * NST + 2 + 4 * NBUF) * 8 + 8 <= BARS_BYTES, "barrier area");
   const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
   const int cluster_id = blockIdx.x / NCTA, nclusters = gridDim.x / NCTA;
 
@@ -441,12 +456,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_units = a.num_qgroups * a.P;
-  // Unit order.  Partition-major (default): all clusters stream the same database range together, so a tile is read
-  // from DRAM once per round and served from L2 to everybody else.  Query-major (B200IR_GEMM_OPT bit 2: the P partitions
-  // of a query group run at the same time and pool their candidates through the shared thresholds sooner) was measured
-  // 39 % SLOWER on the headline shape (12.28 vs 8.82 ms, also at k = 10): P concurrent streams at a fixed 91 MB stride
-  // lose the L2 sharing and more than eat the shorter cold phase.  Kept as a switch for the record.
-  const bool part_major = (a.opt & 4) == 0;
+  // Unit order.  Partition-major: all clusters stream the same database range together, so a tile is read from DRAM once
+  // per round and served from L2 to everybody else.  Query-major (-DGEMM_QUERY_MAJOR=1: the P partitions of a query
+  // group run at the same time and pool their candidates through the shared thresholds sooner) was measured 39 % SLOWER
+  // on the headline shape (12.28 vs 8.82 ms, also at k = 10): P concurrent streams at a fixed 91 MB stride lose the L2
+  // sharing and more than eat the shorter cold phase.  Kept as a compile-time switch for the record.
+#ifndef GEMM_QUERY_MAJOR
+#define GEMM_QUERY_MAJOR 0
+#endif
+  constexpr bool part_major = GEMM_QUERY_MAJOR == 0;
   auto unit_qgroup = [&](int unit) { return part_major ? unit % a.num_qgroups : unit / a.P; };
   auto unit_part = [&](int unit) { return part_major ? unit / a.num_qgroups : unit % a.P; };
 
@@ -457,19 +475,21 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int unit = cluster_id; unit < num_units; unit += nclusters, ++uiter) {
         const int qt = unit_qgroup(unit) * NCTA + int(rank), p = unit_part(unit);
         long long t0 = DBG_T0();
-        mbar_wait(A_EMPTY, (uiter & 1) ^ 1);                   // previous unit's MMAs are done with A
-        DBG_ADD(1, t0);
-        if (rank == 0) mbar_expect_tx(A_FULL, uint32_t(NCTA) * uint32_t(a.num_kb) * A_KB_BYTES);
-        for (int kb = 0; kb < a.num_kb; ++kb) {
-          if constexpr (NCTA == 2) tma_load_2d_2cta(smem_u32(sA + kb * A_KB_BYTES), &tmA, A_FULL, kb * BK, qt * BM);
-          else tma_load_2d(smem_u32(sA + kb * A_KB_BYTES), &tmA, A_FULL, kb * BK, qt * BM);
+        if constexpr (ARES) {
+          mbar_wait(A_EMPTY, (uiter & 1) ^ 1);                   // previous unit's MMAs are done with A
+          DBG_ADD(1, t0);
+          if (rank == 0) mbar_expect_tx(A_FULL, uint32_t(NCTA) * uint32_t(a.num_kb) * A_KB_BYTES);
+          for (int kb = 0; kb < a.num_kb; ++kb) {
+            if constexpr (NCTA == 2) tma_load_2d_2cta(smem_u32(sA + kb * A_KB_BYTES), &tmA, A_FULL, kb * BK, qt * BM);
+            else tma_load_2d(smem_u32(sA + kb * A_KB_BYTES), &tmA, A_FULL, kb * BK, qt * BM);
+          }
         }
         const int tile0 = p * a.tiles_per_part;
         const int tile1 = min(a.total_tiles, tile0 + a.tiles_per_part);
         for (int t = tile0; t < tile1; ++t, ++titer) {
           for (int kb = 0; kb < a.num_kb; ++kb) {
 #pragma unroll
-            for (int part = 0; part < NT; ++part, ++kiter) {          // NT = 3: x_hi, x_lo, q_lo
+            for (int part = 0; part < SLOTS; ++part, ++kiter) {       // resident A: x [, x_lo, q_lo]; streamed A: x, q | x_hi, q_hi, x_lo, q_lo
               const int s = kiter % NST;
               const uint32_t ph = (kiter / NST) & 1;
               t0 = DBG_T0();
@@ -477,7 +497,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               DBG_ADD(0, t0);
               if (rank == 0) mbar_expect_tx(B_FULL(s), B_STAGE_BYTES);                  // both halves land on the leader's barrier
               const uint32_t dst = smem_u32(sB + s * STAGE_BYTES);
-              if constexpr (NT == 3) {
+              if constexpr (!ARES) {
+                const bool is_q = (part & 1) != 0;                    // odd slots carry this CTA's query k-block
+                const CUtensorMap* map = is_q ? (part == 1 ? &tmA : &tmA2) : (part == 0 ? &tmB : &tmB2);
+                if (is_q) tma_load_2d_2cta(dst, map, B_FULL(s), kb * BK, qt * BM);
+                else tma_load_2d_2cta(dst, map, B_FULL(s), kb * BK, t * BN + int(rank) * BN_CTA);
+              } else if constexpr (NT == 3) {
                 if (part == 2) tma_load_2d_2cta(dst, &tmA2, B_FULL(s), kb * BK, qt * BM);
                 else tma_load_2d_2cta(dst, part == 0 ? &tmB : &tmB2, B_FULL(s), kb * BK, t * BN + int(rank) * BN_CTA);
               } else if constexpr (NCTA == 2) {
@@ -517,9 +542,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (uiter == 0) a.dbg[blockIdx.x * 16 + 14] = (unsigned long long)now;
         }
         long long t0 = DBG_T0();
-        mbar_wait(A_FULL, uiter & 1);
-        DBG_ADD(5, t0);
-        tc_fence_after();
+        if constexpr (ARES) {
+          mbar_wait(A_FULL, uiter & 1);
+          DBG_ADD(5, t0);
+          tc_fence_after();
+        }
         for (int t = tile0; t < tile1; ++t, ++titer) {
           const int buf = titer % NBUF;
           t0 = DBG_T0();
@@ -529,7 +556,44 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t tmem_d = tmem_base + uint32_t(buf * BN);
           for (int kb = 0; kb < a.num_kb; ++kb) {
             const uint32_t a_addr = smem_u32(sA + kb * A_KB_BYTES);
-            if constexpr (NT == 3) {
+            if constexpr (!ARES) {
+              // streamed A: slot order x[_hi], q[_hi] (, x_lo, q_lo); every slot has its own full / empty barrier
+              uint32_t sl[SLOTS], phs[SLOTS];
+              int sidx[SLOTS];
+#pragma unroll
+              for (int j = 0; j < SLOTS; ++j) {
+                sidx[j] = int((kiter + j) % NST);
+                phs[j] = ((kiter + j) / NST) & 1;
+                sl[j] = smem_u32(sB + sidx[j] * STAGE_BYTES);
+              }
+              kiter += SLOTS;
+              auto wait_slot = [&](int j) { t0 = DBG_T0(); mbar_wait(B_FULL(sidx[j]), phs[j]); DBG_ADD(3, t0); };
+              auto mma4 = [&](uint32_t aa, uint32_t bb, bool first) {
+#pragma unroll
+                for (int k4 = 0; k4 < BK / UMMA_K; ++k4)
+                  tc_mma_bf16_2cta(tmem_d, make_smem_desc(aa + k4 * UMMA_K * 2), make_smem_desc(bb + k4 * UMMA_K * 2), kInstrDesc2,
+                                   (first && (kb | k4) == 0) ? 0u : 1u);
+              };
+              wait_slot(0);
+              wait_slot(1);
+              tc_fence_after();
+              mma4(sl[1], sl[0], true);                                // q[_hi] . x[_hi]
+              if constexpr (NT == 3) {
+                wait_slot(2);
+                tc_fence_after();
+                mma4(sl[1], sl[2], false);                             // q_hi . x_lo
+                tc_commit_2cta(B_EMPTY(sidx[2]));
+                tc_commit_2cta(B_EMPTY(sidx[1]));
+                wait_slot(3);
+                tc_fence_after();
+                mma4(sl[3], sl[0], false);                             // q_lo . x_hi
+                tc_commit_2cta(B_EMPTY(sidx[0]));
+                tc_commit_2cta(B_EMPTY(sidx[3]));
+              } else {
+                tc_commit_2cta(B_EMPTY(sidx[0]));
+                tc_commit_2cta(B_EMPTY(sidx[1]));
+              }
+            } else if constexpr (NT == 3) {
               // slots: s0 = x_hi, s1 = x_lo, s2 = q_lo of this k-block
               const int s0 = kiter % NST, s1 = (kiter + 1) % NST, s2 = (kiter + 2) % NST;
               const uint32_t ph0 = (kiter / NST) & 1, ph1 = ((kiter + 1) / NST) & 1, ph2 = ((kiter + 2) / NST) & 1;
@@ -585,7 +649,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if constexpr (NCTA == 2) tc_commit_2cta(T_FULL(buf)); else tc_commit(T_FULL(buf));    // accumulator complete -> epilogue
         }
-        if constexpr (NCTA == 2) tc_commit_2cta(A_EMPTY); else tc_commit(A_EMPTY);
+        if constexpr (ARES) { if constexpr (NCTA == 2) tc_commit_2cta(A_EMPTY); else tc_commit(A_EMPTY); }
         if (a.dbg && unit + nclusters >= num_units)              // total issue time of this cluster (slot 11)
           a.dbg[blockIdx.x * 16 + 11] = (unsigned long long)(clock64() - (long long)a.dbg[blockIdx.x * 16 + 14]);
       }
@@ -843,7 +907,8 @@ struct Certify {
 // strictly better than that bound, no dropped row can enter or tie the top-k and the result equals the exact scan's.
 // Otherwise (near-ties denser than the kp - k margin, duplicates, huge-norm outliers) the query is appended to
 // fb_list and re-done by the exact CUDA-core scan.
-template <int E, typename T>
+// QJ: 256-element slices of a row each lane keeps in registers (2: D <= 512, 8: D <= 2048)
+template <int E, typename T, int QJ>
 __global__ void __launch_bounds__(128)
 gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __restrict__ thr_g, const T* __restrict__ Q,
                      const T* __restrict__ X, int nq, int D, int P, int kp, int k, int mode, int rerank, MetricParams mp,
@@ -899,12 +964,12 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
   }
   const bool list_full = kept >= kp;
 
-  // query row in registers: lane holds elements [8*(lane + 32 j), +8), j = 0, 1 (D <= 512)
+  // query row in registers: lane holds elements [8*(lane + 32 j), +8), j < QJ
   const T* qrow = Q + int64_t(q) * D;
-  float qf[2][8];
+  float qf[QJ][8];
   float qss = 0.f;
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < QJ; ++j) {
     const int d = (lane + 32 * j) * 8;
 #pragma unroll
     for (int e = 0; e < 8; ++e) qf[j][e] = 0.f;
@@ -929,7 +994,7 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
         const T* xrow = X + int64_t(idx) * D;
         float dot = 0.f, xss = 0.f, d2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < QJ; ++j) {
           const int d = (lane + 32 * j) * 8;
           if (d < D) {
             float xf[8];
@@ -1043,6 +1108,7 @@ static IndexLayout index_layout(int dtype, int64_t N, int D) {
 
 struct Plan {
   int num_qtiles, num_qgroups, ncta, total_tiles, P, tiles_per_part, kp, cap, grid, num_kb;
+  bool ares;                                    // query tile resident (D <= 512) or streamed
   size_t off_thr, off_lvl, off_cand, off_partial, off_fb, off_qhi, off_qlo, off_index, off_fbws, total_bytes;
 };
 
@@ -1064,8 +1130,9 @@ static int gemm_ncta(int dtype) {
 
 static Plan make_plan(int dtype, int64_t nq, int64_t N, int D, int k, int flags, int sms, bool internal_index, size_t fallback_bytes) {
   Plan pl{};
-  pl.ncta = gemm_ncta(dtype);
   pl.num_kb = (D + BK - 1) / BK;
+  pl.ares = pl.num_kb <= MAX_KB;
+  pl.ncta = pl.ares ? gemm_ncta(dtype) : 2;
   pl.num_qtiles = int(ceil_div64(nq, BM));
   pl.num_qgroups = (pl.num_qtiles + pl.ncta - 1) / pl.ncta;
   const int nclusters_max = sms / pl.ncta;
@@ -1141,7 +1208,7 @@ static int clamp_sms() {
 bool gemm_path_supported(int metric, int dtype, int64_t nq, int64_t N, int D, int k, int flags) {
   if (dtype != B200IR_BF16 && dtype != B200IR_F32) return false;
   if (!(metric == B200IR_L2 || metric == B200IR_COS_SIM || metric == B200IR_COS_DIST || metric == B200IR_ANGLE)) return false;
-  if (D % 8 != 0 || D > gemm::MAX_KB * gemm::BK || D < 16) return false;
+  if (D % 8 != 0 || D > gemm::MAX_D_STREAM || D < 16) return false;
   if (nq < 32 || N < 4 * gemm::BN) return false;      // tiny problems stay on the scan path
   if (k > 224) return false;
   return true;
@@ -1152,7 +1219,7 @@ size_t gemm_fallback_counter_offset(int dtype, int64_t nq, int64_t N, int D, int
 }
 
 size_t gemm_index_bytes(int dtype, int64_t N, int D) {
-  if (N <= 0 || D <= 0 || D % 8 != 0 || D > gemm::MAX_KB * gemm::BK || D < 16) return 0;
+  if (N <= 0 || D <= 0 || D % 8 != 0 || D > gemm::MAX_D_STREAM || D < 16) return 0;
   return gemm::index_layout(dtype, N, D).total_bytes;
 }
 
@@ -1229,12 +1296,13 @@ int run_gemm_topk(int metric, int dtype, const void* Q, int64_t nq, const void* 
     ProfileScope ps(PT_GEMM, st);
     cudaError_t e;
     auto launch = [&](auto kern, int ncta) -> cudaError_t {
-      cudaError_t le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+      const int smem_bytes = pl.ares ? SMEM_TOTAL : SMEM_TOTAL_STREAM;
+      cudaError_t le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
       if (le != cudaSuccess) return le;
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(unsigned(pl.grid));
       cfg.blockDim = dim3(THREADS);
-      cfg.dynamicSmemBytes = SMEM_TOTAL;
+      cfg.dynamicSmemBytes = smem_bytes;
       cfg.stream = st;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1245,18 +1313,28 @@ int run_gemm_topk(int metric, int dtype, const void* Q, int64_t nq, const void* 
       cfg.numAttrs = 1;
       return cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, tmB2, a);
     };
-    if (f32) {
-      if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 2, 3>, 2);
-      else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 2, 3>, 2);
-      else e = launch(gemm_topk_kernel<MODE_L2, 2, 3>, 2);
+    if (!pl.ares) {
+      if (f32) {
+        if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 2, 3, false>, 2);
+        else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 2, 3, false>, 2);
+        else e = launch(gemm_topk_kernel<MODE_L2, 2, 3, false>, 2);
+      } else {
+        if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 2, 1, false>, 2);
+        else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 2, 1, false>, 2);
+        else e = launch(gemm_topk_kernel<MODE_L2, 2, 1, false>, 2);
+      }
+    } else if (f32) {
+      if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 2, 3, true>, 2);
+      else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 2, 3, true>, 2);
+      else e = launch(gemm_topk_kernel<MODE_L2, 2, 3, true>, 2);
     } else if (pl.ncta == 2) {
-      if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 2, 1>, 2);
-      else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 2, 1>, 2);
-      else e = launch(gemm_topk_kernel<MODE_L2, 2, 1>, 2);
+      if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 2, 1, true>, 2);
+      else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 2, 1, true>, 2);
+      else e = launch(gemm_topk_kernel<MODE_L2, 2, 1, true>, 2);
     } else {
-      if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 1, 1>, 1);
-      else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 1, 1>, 1);
-      else e = launch(gemm_topk_kernel<MODE_L2, 1, 1>, 1);
+      if (mode == MODE_COS) e = launch(gemm_topk_kernel<MODE_COS, 1, 1, true>, 1);
+      else if (mode == MODE_ABSCOS) e = launch(gemm_topk_kernel<MODE_ABSCOS, 1, 1, true>, 1);
+      else e = launch(gemm_topk_kernel<MODE_L2, 1, 1, true>, 1);
     }
     if (e != cudaSuccess) return int(e);
     e = cudaGetLastError();
@@ -1289,20 +1367,20 @@ int run_gemm_topk(int metric, int dtype, const void* Q, int64_t nq, const void* 
     // analysis; tests/test_gpu_tensor_fp32.py measures the actual worst error against them.
     Certify cert{f32 ? 6.1035156e-5f : 1.5258789e-5f, reinterpret_cast<const unsigned int*>(index + IL.off_max),
                  rerank ? fb_count : nullptr, fb_list};
+    auto fin = [&](auto kern, auto Qp, auto Xp) {
+      kern<<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qp, Xp, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, cert, out_score, out_idx);
+    };
+    const bool wide = D > 512, big = pl.kp > 128;
     if (f32) {
-      const float* Qf = static_cast<const float*>(Q);
-      const float* Xf = static_cast<const float*>(X);
-      if (pl.kp <= 128)
-        gemm_finalize_kernel<8, float><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qf, Xf, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, cert, out_score, out_idx);
-      else
-        gemm_finalize_kernel<16, float><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qf, Xf, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, cert, out_score, out_idx);
+      const float* Qp = static_cast<const float*>(Q);
+      const float* Xp = static_cast<const float*>(X);
+      if (!wide) { if (!big) fin(gemm_finalize_kernel<8, float, 2>, Qp, Xp); else fin(gemm_finalize_kernel<16, float, 2>, Qp, Xp); }
+      else { if (!big) fin(gemm_finalize_kernel<8, float, 8>, Qp, Xp); else fin(gemm_finalize_kernel<16, float, 8>, Qp, Xp); }
     } else {
-      const __nv_bfloat16* Qb = static_cast<const __nv_bfloat16*>(Q);
-      const __nv_bfloat16* Xb = static_cast<const __nv_bfloat16*>(X);
-      if (pl.kp <= 128)
-        gemm_finalize_kernel<8, __nv_bfloat16><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, cert, out_score, out_idx);
-      else
-        gemm_finalize_kernel<16, __nv_bfloat16><<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qb, Xb, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, cert, out_score, out_idx);
+      const __nv_bfloat16* Qp = static_cast<const __nv_bfloat16*>(Q);
+      const __nv_bfloat16* Xp = static_cast<const __nv_bfloat16*>(X);
+      if (!wide) { if (!big) fin(gemm_finalize_kernel<8, __nv_bfloat16, 2>, Qp, Xp); else fin(gemm_finalize_kernel<16, __nv_bfloat16, 2>, Qp, Xp); }
+      else { if (!big) fin(gemm_finalize_kernel<8, __nv_bfloat16, 8>, Qp, Xp); else fin(gemm_finalize_kernel<16, __nv_bfloat16, 8>, Qp, Xp); }
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return int(e);

@@ -180,3 +180,27 @@ def test_full_size_fp32_tensor_path(ops):
         truth = OM.pairwise_f64(Q[sample].cpu().numpy(), Xh, metric)
         disputed = check_topk(s_h[sample], i_h[sample], truth, k, OM.DESCENDING[metric], **_tol(metric))
         assert disputed <= 12, disputed
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+@pytest.mark.parametrize("nq,N,D,k", [(64, 5000, 768, 10), (40, 3000, 1024, 100), (33, 2100, 2048, 20), (256, 50_000, 1024, 224),
+                                      (70, 4000, 520, 16)])
+def test_wide_rows_streamed_tensor_path(ops, bf16, nq, N, D, k):
+    """D > 512: the query tile no longer fits in shared memory next to the ring, so the query k-blocks are streamed with
+    the database k-blocks (A-streamed kernel variant) - still tcgen05 + exact re-rank + certificate."""
+    import torch
+    Q = synth.gaussian(nq, D, 51)
+    X = synth.gaussian(N, D, 52)
+    X[9] = Q[2]
+    if bf16:
+        Q, X = OM.bf16_round(Q), OM.bf16_round(X)
+        Qd, Xd = torch.from_numpy(Q).cuda().bfloat16(), torch.from_numpy(X).cuda().bfloat16()
+    else:
+        Qd, Xd = torch.from_numpy(Q).cuda(), torch.from_numpy(X).cuda()
+    for metric in ("cosine_similarity", "l2"):
+        s, i = ops.topk(Qd, Xd, metric, k)
+        assert ops.last_fallback_count() is not None, "wide rows did not take the tensor-core path"
+        truth = OM.pairwise_f64(Q, X, metric)
+        disputed = check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, k, OM.DESCENDING[metric], **_tol(metric))
+        assert disputed <= max(1, nq * k // 200), f"{disputed} disputed ranks"
+        assert i[2, 0].item() == 9
