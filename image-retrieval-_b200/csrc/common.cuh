@@ -98,6 +98,24 @@ __device__ __forceinline__ void warp_sort(K (&k)[E], int lane) {
   }
 }
 
+// The same sort as ONE out-of-line function (keys travel in registers, by value): a kernel that sorts at several places
+// otherwise carries one ~30 KB copy of the network per call site and becomes instruction-fetch bound.
+template <int E> struct KeyRegs { uint64_t k[E]; };
+template <int E>
+__device__ __noinline__ KeyRegs<E> warp_sort_call(KeyRegs<E> v, int lane) {
+  warp_sort<E>(v.k, lane);
+  return v;
+}
+template <int E>
+__device__ __forceinline__ void warp_sort_shared(uint64_t (&k)[E], int lane) {
+  KeyRegs<E> v;
+#pragma unroll
+  for (int e = 0; e < E; ++e) v.k[e] = k[e];
+  v = warp_sort_call<E>(v, lane);
+#pragma unroll
+  for (int e = 0; e < E; ++e) k[e] = v.k[e];
+}
+
 // Final pass of the sort above on its own: `k` (32*E keys, blocked) holds a bitonic sequence, result ascending.
 template <int E, typename K>
 __device__ __forceinline__ void warp_bitonic_merge(K (&k)[E], int lane) {

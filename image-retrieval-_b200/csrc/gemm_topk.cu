@@ -944,7 +944,7 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
         const int i = lane * E + e;
         if (i >= kept) r[e] = (i - kept) < fill ? stage[i - kept] : kKeyInf;
       }
-      warp_sort<E>(r, lane);
+      warp_sort_shared<E>(r, lane);
       kept = min(kept + fill, kp);
       fill = 0;
 #pragma unroll
@@ -1031,7 +1031,7 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
   }
 #pragma unroll
   for (int e = 0; e < E; ++e) if (lane * E + e >= kp) r[e] = kKeyInf;
-  warp_sort<E>(r, lane);
+  warp_sort_shared<E>(r, lane);
   if (rerank && cert.fb_count != nullptr && list_full) {
     uint64_t kk = kKeyInf;
 #pragma unroll
@@ -1051,7 +1051,7 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
     }
     if (!ok && lane == 0) cert.fb_list[atomicAdd(cert.fb_count, 1)] = q;
   }
-  emit_topk<E>(r, lane, k, mp, index_offset, out_score, out_idx, int64_t(q));
+  emit_topk<E, true>(r, lane, k, mp, index_offset, out_score, out_idx, int64_t(q));
 }
 
 // ------------------------------------------------------------------------------------ host side

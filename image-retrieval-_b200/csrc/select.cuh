@@ -10,7 +10,8 @@ namespace b200ir {
 // metric's reference-normalised score, then re-sorted by (score, index): transforms such as 1 - cos, sqrt or
 // arccos can round distinct rank values to the same fp32 score, and the reference's stable sort orders equal
 // scores by index (app_pipeline.py:171-172, image_search.py:199-219).
-template <int E>
+// SHARED_SORT: sort through the out-of-line copy of the network (kernels that sort at several places)
+template <int E, bool SHARED_SORT = false>
 __device__ __forceinline__ void emit_topk(uint64_t (&r)[E], int lane, int k, const MetricParams& mp, int64_t index_offset,
                                           float* __restrict__ out_score, int64_t* __restrict__ out_idx, int64_t q) {
   const bool desc = metric_descending(mp.metric);
@@ -24,7 +25,7 @@ __device__ __forceinline__ void emit_topk(uint64_t (&r)[E], int lane, int k, con
       r[e] = kKeyInf;
     }
   }
-  warp_sort<E>(r, lane);
+  if constexpr (SHARED_SORT) warp_sort_shared<E>(r, lane); else warp_sort<E>(r, lane);
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int i = lane * E + e;
