@@ -204,3 +204,25 @@ def test_wide_rows_streamed_tensor_path(ops, bf16, nq, N, D, k):
         disputed = check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, k, OM.DESCENDING[metric], **_tol(metric))
         assert disputed <= max(1, nq * k // 200), f"{disputed} disputed ranks"
         assert i[2, 0].item() == 9
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_tensor_path_results_do_not_depend_on_timing(ops, bf16):
+    """compute-sanitizer is closed on this pool (profiles/r2_sanitizer_closed.txt), so the lock-free parts of the
+    tcgen05 epilogue (two-ended candidate lists, named-barrier hand-off, thresholds imported from other CTAs at
+    arbitrary moments) are checked by repetition instead: which candidates a list holds at any instant depends on
+    timing, the final result must not.  Twelve runs of a many-CTA search, all bit-identical."""
+    import torch
+    g = torch.Generator(device="cuda")
+    g.manual_seed(99)
+    X = torch.randn((300_000, 512), generator=g, device="cuda")
+    Q = torch.randn((1500, 512), generator=g, device="cuda")
+    if bf16:
+        X, Q = X.bfloat16(), Q.bfloat16()
+    idx = ops.prepare_index(X)
+    for metric in ("cosine_similarity", "l2"):
+        s0, i0 = ops.topk(Q, idx, metric, 100)
+        s0, i0 = s0.clone(), i0.clone()
+        for _ in range(11):
+            s, i = ops.topk(Q, idx, metric, 100)
+            assert torch.equal(i, i0) and torch.equal(s, s0), metric
