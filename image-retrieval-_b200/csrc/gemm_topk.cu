@@ -999,20 +999,24 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
           if (d < D) {
             float xf[8];
             load8<T>(xrow + d, xf);
+            if (mode == MODE_L2) {                                 // warp-uniform: only the sums the metric needs
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              dot = fmaf(xf[t], qf[j][t], dot);
-              xss = fmaf(xf[t], xf[t], xss);
-              const float df = qf[j][t] - xf[t];
-              d2 = fmaf(df, df, d2);
+              for (int t = 0; t < 8; ++t) { const float df = qf[j][t] - xf[t]; d2 = fmaf(df, df, d2); }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 8; ++t) { dot = fmaf(xf[t], qf[j][t], dot); xss = fmaf(xf[t], xf[t], xss); }
             }
           }
         }
+        if (mode == MODE_L2) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          dot += __shfl_xor_sync(0xffffffffu, dot, o);
-          xss += __shfl_xor_sync(0xffffffffu, xss, o);
-          d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+          for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        } else {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            xss += __shfl_xor_sync(0xffffffffu, xss, o);
+          }
         }
         if (mode == MODE_L2) rank = d2;
         else {
