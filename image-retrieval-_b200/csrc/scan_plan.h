@@ -122,16 +122,20 @@ inline ScanPlan make_scan_plan(int metric, int dtype, int64_t nq, int64_t N, int
   const int64_t target = int64_t(kNumSMs) * ctas_per_sm;
   int64_t P = target / pl.G;
   if (P < 1) P = 1;
-  if (pl.G * 2 > target) {
-    // many query groups (batch regime): G x P CTAs run in waves of `target`; pick the smallest P whose last wave is
-    // at least 95 % full (G = 128, target = 296: P = 2 leaves 13.5 % of the slots idle, P = 9 leaves 2.7 %)
-    const int64_t max_p = N / (int64_t(16) * kScanThreads * pl.TR) > 1 ? N / (int64_t(16) * kScanThreads * pl.TR) : 1;
-    double best_eff = 0.0;
-    for (int64_t cand = 1; cand <= 64 && cand <= max_p; ++cand) {
-      const int64_t ctas = pl.G * cand;
-      const double eff = double(ctas) / double(ceil_div64(ctas, target) * target);
-      if (eff > best_eff + 1e-9) { best_eff = eff; P = cand; }
-      if (eff >= 0.95) break;
+  {
+    // G x P CTAs run in waves of `target`: when the default P leaves more than 5 % of the last wave idle (G = 128,
+    // target = 296: P = 2 fills 86 %), take the smallest P whose last wave is at least 95 % full (P = 9: 97 %)
+    const int64_t ctas0 = pl.G * P;
+    const double eff0 = double(ctas0) / double(ceil_div64(ctas0, target) * target);
+    if (eff0 < 0.95 && pl.G > 1) {
+      const int64_t max_p = N / (int64_t(16) * kScanThreads * pl.TR) > 1 ? N / (int64_t(16) * kScanThreads * pl.TR) : 1;
+      double best_eff = eff0;
+      for (int64_t cand = 1; cand <= 64 && cand <= max_p; ++cand) {
+        const int64_t ctas = pl.G * cand;
+        const double eff = double(ctas) / double(ceil_div64(ctas, target) * target);
+        if (eff > best_eff + 1e-9) { best_eff = eff; P = cand; }
+        if (eff >= 0.95) break;
+      }
     }
   }
   const int tile_rows = kScanThreads * pl.TR;

@@ -86,12 +86,26 @@ def _dtype_id(t):
 
 
 def _workspace(nbytes, dev):
+    """Scratch buffer of the C ABI calls, cached per (device, stream).  It grows on demand and is given back when a call
+    needs less than a quarter of a large (> 256 MB) buffer, so one big search does not pin its scratch for ever;
+    release_workspaces() drops everything (e.g. between workloads)."""
     key = (dev.index, torch.cuda.current_stream().cuda_stream)
     ws = _workspaces.get(key)
-    if ws is None or ws.numel() < nbytes:
+    if ws is None or ws.numel() < nbytes or (ws.numel() > (256 << 20) and nbytes * 4 < ws.numel()):
+        _workspaces.pop(key, None)
+        ws = None
         ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
+        if len(_workspaces) >= 16:                 # streams come and go: do not accumulate one buffer per dead stream
+            _workspaces.clear()
         _workspaces[key] = ws
     return ws
+
+
+def release_workspaces():
+    """Free every cached scratch buffer (they are re-created on the next call)."""
+    global _last_topk
+    _workspaces.clear()
+    _last_topk = None
 
 
 def _weights(params):
