@@ -522,7 +522,7 @@ def run_headline(args):
                 r = measure_side(a2)
                 key = w + "".join(f"_{k_}{v_}" for k_, v_ in kw.items())
                 side[key] = {k_: r[k_] for k_ in ("metric", "value", "unit", "ms_per_step", "steps", "gpu_launches", "clocks", "roofline",
-                                                 "config") if k_ in r}
+                                                 "config", "dtype", "kernels_ms", "fallback_queries_per_step") if k_ in r}
             except Exception as ex:  # noqa: BLE001
                 side[w] = {"error": repr(ex)[:300]}
             torch.cuda.empty_cache()
