@@ -1214,7 +1214,7 @@ bool gemm_path_supported(int metric, int dtype, int64_t nq, int64_t N, int D, in
   if (!(metric == B200IR_L2 || metric == B200IR_COS_SIM || metric == B200IR_COS_DIST || metric == B200IR_ANGLE)) return false;
   if (D % 8 != 0 || D > gemm::MAX_D_STREAM || D < 16) return false;
   if (nq < 32 || N < 4 * gemm::BN) return false;      // tiny problems stay on the scan path
-  if (k > 224) return false;
+  if (k > 240) return false;                          // k' = k + k/16 must fit half a candidate list (cap / 2 = 256)
   return true;
 }
 

@@ -144,7 +144,8 @@ class EnhancedTextImageSearcher:
             return [[] for _ in range(Q.shape[0])]
         kc = max(1, min(int(top_k) * 3, len(paths)))
         self._check_rerank_limit(kc, "search_batch")                      # the post-filter kernel holds the same 1024 rows
-        s, i = ops.topk(Q, X, "cosine_similarity", kc)                    # candidate stage (:88-95)
+        target = self.collection.prepared() if hasattr(self.collection, "prepared") else X     # norms / split planes built once per store version
+        s, i = ops.topk(Q, target, "cosine_similarity", kc)               # candidate stage (:88-95)
         if use_optimized_similarity:
             # re-score the cosine candidates (:103-107) and stable-sort them (:115) on the device: get_all_metrics of every
             # (query, candidate) pair in one launch, weighted sum + ordering in a second one

@@ -63,6 +63,18 @@ class EmbeddingStore:
     def device_matrix(self):
         return self.flush()
 
+    def prepared(self):
+        """The matrix with its per-store search state (ops.PreparedIndex: row norms, bf16 planes of an fp32 store), built
+        once per content version - what a query BATCH against a static store should be searched with."""
+        m = self.flush()
+        if m is None:
+            return None
+        key = (self.version, m.data_ptr(), tuple(m.shape))
+        if getattr(self, "_prepared_key", None) != key:
+            self._prepared = ops.prepare_index(m)
+            self._prepared_key = key
+        return self._prepared
+
     def set_path(self, row, path):
         """Rename a stored row (keeps the de-duplication groups of the searchers in step)."""
         self.paths[row] = str(path)

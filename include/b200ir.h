@@ -103,7 +103,7 @@ int b200ir_topk(int metric, int dtype, const void* Q, int64_t nq, const void* X,
 
 /*
  * Exactness of the tensor-core path.  L2 / cosine-family searches of bf16 and fp32 stores (D % 8 == 0, D <= 512,
- * nq >= 32, N >= 1024, k <= 224) select kp > k candidates per query on tcgen05 (fp32 stores: three-term bf16 split),
+ * nq >= 32, N >= 1024, k <= 240) select kp > k candidates per query on tcgen05 (fp32 stores: three-term bf16 split),
  * re-rank them with exact fp32 arithmetic on the original rows and CERTIFY the result: if a dropped row could still
  * reach the k-th exact score within the proven error of the tensor-core pass, the query is re-done by the exact
  * CUDA-core scan in the same call.  Results therefore equal the scan's; the int32 at this byte offset of the

@@ -32,7 +32,7 @@ def _tol(metric):
 
 @pytest.mark.parametrize("metric", ["cosine_similarity", "cosine_distance", "angular_distance", "l2"])
 @pytest.mark.parametrize("nq,N,D,k", [(64, 4096, 512, 10), (300, 50_000, 512, 100), (129, 20_001, 256, 100),
-                                      (40, 3000, 96, 5), (200, 9000, 40, 224)])
+                                      (40, 3000, 96, 5), (200, 9000, 40, 224), (100, 30_000, 128, 240)])
 def test_fp32_tensor_path_vs_oracle(ops, metric, nq, N, D, k):
     Q = synth.gaussian(nq, D, 11)
     X = synth.gaussian(N, D, 12)
