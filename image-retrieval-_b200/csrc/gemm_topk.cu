@@ -218,6 +218,8 @@ __device__ __forceinline__ void import_threshold(const uint32_t* thr_g_q, float&
 // every unit of the query.  Level 0 alone (the best k'-th value of any single partition) is what a per-unit list can
 // give; the deeper levels make the threshold track the union of the partitions seen so far instead of one of them.
 constexpr int kLevels = 4;
+__device__ __forceinline__ void publish_level_values(const uint32_t (&mine)[kLevels], int lane, uint32_t* thr_g_q, uint32_t* lvl_q,
+                                                     int p, int P);
 template <int E>
 __device__ __forceinline__ void publish_levels(const uint64_t (&r)[E], int n, int kp, int lane, uint32_t* thr_g_q, uint32_t* lvl_q,
                                                int p, int P) {
@@ -232,6 +234,13 @@ __device__ __forceinline__ void publish_levels(const uint64_t (&r)[E], int n, in
     hi = __shfl_sync(0xffffffffu, hi, src_lane);
     mine[j] = n >= m ? hi : 0xffffffffu;
   }
+  publish_level_values(mine, lane, thr_g_q, lvl_q, p, P);
+}
+
+// `mine[j]`: a rank value (ordered bits) such that this partition holds at least ceil(kp / 2^j) candidates at least that
+// good (0xffffffff: no such statement yet)
+__device__ __forceinline__ void publish_level_values(const uint32_t (&mine)[kLevels], int lane, uint32_t* thr_g_q, uint32_t* lvl_q,
+                                                     int p, int P) {
   if (lvl_q == nullptr) {                                     // more partitions than lanes: level 0 only
     if (lane == 0 && mine[0] != 0xffffffffu) atomicMin(thr_g_q, mine[0]);
     return;
@@ -318,12 +327,83 @@ __device__ __noinline__ void compact_merge(uint64_t* list, int cap, int kp, int 
   __syncwarp();
 }
 
+// Compaction by SELECTION (the in-loop compactions; the unit end still sorts): the list only has to shrink to its best
+// ~kp keys and yield a threshold, it does not have to be ordered.  A bisection on the 32-bit rank value (one
+// __reduce_add_sync count per step, ~10-14 steps for a 200-key list) finds a pivot with at least kp keys at or below
+// it; the survivors are ballot-compacted to the front with the WORST survivor parked at position kp - 1, where the
+// owner threads read their new threshold (at least kp rows are at least that good, so anything not strictly better
+// cannot enter).  The counts seen along the bisection give valid statements for the shared threshold levels for free.
+// ~400 instructions instead of the 1300-2500 of a sort / merge; falls back to the sorter when ties keep the pivot
+// from separating (more than kp + 48 survivors).
+template <int E>
+__device__ __noinline__ bool compact_select(uint64_t* list, int cap, int kp, int n0, int n1, unsigned short* cnt_front,
+                                            unsigned short* cnt_back, unsigned short* srt, int lane, uint32_t* thr_g_q,
+                                            uint32_t* lvl_q, int p, int P) {
+  const int n = n0 + n1;
+  uint64_t r[E];
+  uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = lane * E + e;
+    r[e] = i < n0 ? list[i] : (i < n ? list[cap - 1 - (i - n0)] : kKeyInf);
+    if (i < n) { const uint32_t h = uint32_t(r[e] >> 32); lo = min(lo, h); hi = max(hi, h); }
+  }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  int need[kLevels];
+  uint32_t best[kLevels];
+#pragma unroll
+  for (int j = 0; j < kLevels; ++j) { need[j] = (kp + (1 << j) - 1) >> j; best[j] = hi; }     // all n >= kp keys are <= hi
+  uint32_t L = lo, H = hi;                                   // invariant: count(rank <= H) >= kp
+  int cH = n;
+  for (int it = 0; it < 32 && L < H; ++it) {
+    const uint32_t mid = L + ((H - L) >> 1);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c += (r[e] != kKeyInf && uint32_t(r[e] >> 32) <= mid) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+#pragma unroll
+    for (int j = 1; j < kLevels; ++j) if (c >= need[j] && mid < best[j]) best[j] = mid;
+    if (c >= kp) { H = mid; cH = c; if (c <= kp + 8) break; } else L = mid + 1;
+  }
+  if (cH > kp + 48) return false;                            // ties: let the sorter cut by (rank, row)
+  best[0] = H;
+  // worst survivor (largest key at or below the pivot): goes to position kp - 1
+  uint64_t wkey = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) if (r[e] != kKeyInf && uint32_t(r[e] >> 32) <= H && r[e] > wkey) wkey = r[e];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const uint64_t other = shfl_xor_u64(wkey, o); wkey = other > wkey ? other : wkey; }
+  __syncwarp();                                              // every key is in registers before the front is rewritten
+  int base = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const bool keep = r[e] != kKeyInf && uint32_t(r[e] >> 32) <= H && r[e] != wkey;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      int pos = base + __popc(m & ((1u << lane) - 1));
+      pos += pos >= kp - 1 ? 1 : 0;                          // skip the slot reserved for the worst survivor
+      list[pos] = r[e];
+    }
+    base += __popc(m);
+  }
+  if (lane == 0) {
+    list[kp - 1] = wkey;
+    *cnt_front = (unsigned short)(base + 1);
+    *cnt_back = 0;
+    *srt = 0;                                                // nothing is sorted
+  }
+  publish_level_values(best, lane, thr_g_q, lvl_q, p, P);
+  __syncwarp();
+  return true;
+}
+
 // Warp-cooperative compaction of the candidate lists of the query rows in `mask` (bit L = row L of this TMEM lane
 // quarter): sort, keep the best kp, publish the k'-th rank value.  The sorter width follows the list length.
 // If `out` is set the sorted list goes to the unit's output slot instead of back to the scratch list.
 __device__ __forceinline__ void warp_compact(uint64_t* warp_lists, int cap, int kp, unsigned short* cnt_q, uint32_t mask, int lane,
                                              uint64_t* out, int64_t out_stride, int valid_lanes, uint32_t* thr_g_warp,
-                                             uint32_t* lvl_warp, int p, int P) {
+                                             uint32_t* lvl_warp, int p, int P, bool use_select = false) {
   while (mask) {
     const int L = __ffs(mask) - 1;
     mask &= mask - 1;
@@ -338,6 +418,11 @@ __device__ __forceinline__ void warp_compact(uint64_t* warp_lists, int cap, int 
     const int s = cnt_q[64 + L];                               // sorted prefix left by the previous compaction
     const int h = n0 + n1 - s;
     unsigned short *cf = cnt_q + L, *cb = cnt_q + 32 + L, *srt = cnt_q + 64 + L;
+    if (use_select && dst == nullptr && n0 + n1 > kp) {      // in-loop compaction: selection first, the sorter on ties
+      const bool done = n0 + n1 <= 256 ? compact_select<8>(list, cap, kp, n0, n1, cf, cb, srt, lane, thr_g_warp + L, lvl_q, p, P)
+                                       : compact_select<16>(list, cap, kp, n0, n1, cf, cb, srt, lane, thr_g_warp + L, lvl_q, p, P);
+      if (done) continue;
+    }
     if (s > 0 && h <= 128 && kp <= 128) compact_merge<4>(list, cap, kp, s, n0, n1, cf, cb, srt, lane, dst, thr_g_warp + L, lvl_q, p, P);
     else if (s > 0 && h <= 256) compact_merge<8>(list, cap, kp, s, n0, n1, cf, cb, srt, lane, dst, thr_g_warp + L, lvl_q, p, P);
     else if (n0 + n1 <= 256) compact_one<8>(list, cap, kp, n0, n1, cf, cb, srt, lane, dst, thr_g_warp + L, lvl_q, p, P);
@@ -693,7 +778,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (full) {
         const long long tc0 = dbg_me ? clock64() : 0ll;
         const uint32_t mine = alternate_bits(full, half);
-        warp_compact(warp_lists, a.cap, a.kp, cnt_q, mine, lane, nullptr, 0, 32, thr_g_warp, lvl_warp, cur_p, a.P);
+        warp_compact(warp_lists, a.cap, a.kp, cnt_q, mine, lane, nullptr, 0, 32, thr_g_warp, lvl_warp, cur_p, a.P, !(a.opt & 8));
         pair_sync();
         if ((full >> lane) & 1) {
           cnt = int(*mycnt);                                                // kp (or fewer) at the front, 0 at the back
