@@ -8,6 +8,8 @@ contiguous range of database rows and runs the fused distance + top-k locally wi
                (app_pipeline.py:171-172: stable sort -> ties to the lower global index),
   all-gather   of the merged slices when every rank wants the full result (`topk`); a rank that serves
                only its slice of the query stream stops before it (`topk_slice`).
+Small batches (nq * k <= 64 K entries, e.g. the 8-query scans) skip all that: one all-gather of a packed
+[scores | ids] record per rank and a merge of every query on every rank - a single latency-bound collective.
 
 The scan itself is embarrassingly parallel; no other data-path collective exists.  Bytes per rank at
 nq = 10k, k = 100, R = 8: 10.5 MB out + 10.5 MB in for the all-to-all and 1.5 MB / 10.5 MB for the
@@ -108,9 +110,31 @@ class ShardedIndex:
         q0, q1 = query_slice(nq, R, r)
         return ms, mi, q0, q1                                      # rows past q1 - q0 are padding lists
 
+    SMALL_PAYLOAD_ENTRIES = 1 << 16      # nq * k up to this: one packed all-gather beats four latency-bound collectives
+
+    def _topk_small(self, Q, metric, m, k, **kw):
+        """Few queries (e.g. the 8-query L1 / Linf scans): the lists are tiny, so ONE all-gather of a packed record
+        [scores | ids] per rank and a merge of every query on every rank (CUDA operators only)."""
+        R, _ = self._world()
+        Qd = ops.as_device_matrix(Q, dtype=self.X.dtype)
+        nq = Qd.shape[0]
+        score_bytes = -(-nq * k * 4 // 16) * 16
+        rec = -(-(score_bytes + nq * k * 8) // 16) * 16
+        buf = torch.empty(rec, dtype=torch.uint8, device=Qd.device)
+        s = buf[:nq * k * 4].view(torch.float32).view(nq, k)
+        i = buf[score_bytes:score_bytes + nq * k * 8].view(torch.int64).view(nq, k)
+        ops.topk(Qd, self.X, metric, k, index_offset=self.row_begin, out=(s, i), **kw)
+        gathered = torch.empty(R * rec, dtype=torch.uint8, device=Qd.device)
+        dist.all_gather_into_tensor(gathered, buf, group=self.group)
+        return ops.topk_merge_packed(gathered, R, nq, k, score_bytes, m in ops.DESCENDING)
+
     def topk(self, Q, metric, k, **kw):
         """Global top-k over all shards; every rank returns the same (scores (nq, k), indices (nq, k))."""
         R, _ = self._world()
+        if R > 1 and self.local_topk is _default_local and self.merge is _default_merge:
+            nq = 1 if getattr(Q, "ndim", 2) == 1 else Q.shape[0]
+            if nq * k <= self.SMALL_PAYLOAD_ENTRIES:
+                return self._topk_small(Q, metric, ops.metric_id(metric), k, **kw)
         ms, mi, _q0, _q1 = self.topk_slice(Q, metric, k, **kw)
         if R == 1:
             return ms, mi

@@ -33,6 +33,10 @@ def main():
         s1, i1 = ops.topk(Qd, Xd, metric, k)
         s2, i2 = ShardedIndex(Xd[b:e].contiguous(), b).topk(Qd, metric, k)
         same = torch.equal(i1, i2) and torch.equal(s1, s2)
+        # 8 queries: the small-payload path (one packed all-gather)
+        s3, i3 = ops.topk(Qd[:8], Xd, metric, k)
+        s4, i4 = ShardedIndex(Xd[b:e].contiguous(), b).topk(Qd[:8], metric, k)
+        same = same and torch.equal(i3, i4) and torch.equal(s3, s4)
         ok = ok and same
         if rank == 0:
             print(f"{metric:18s} {str(dtype):15s} k={k:3d} sharded==single: {same}")
