@@ -484,9 +484,17 @@ int b200ir_histogram(int colorspace, const uint8_t* img, int64_t B, int H, int W
   }
   ProfileScope ps(PT_HIST, st);
   if (colorspace == B200IR_HSV) {
-    histogram_kernel<true><<<unsigned(B * slices), kHistThreads, 0, st>>>(img, pixels, slices, vector_ok, out_counts);
+    // persistent: two CTAs per SM, each with its own lane-replicated division tables (100 KB of shared memory)
+    int dev = 0, sms = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return int(e);
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return int(e);
+    e = cudaFuncSetAttribute(hsv_histogram_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(HsvSmem)));
+    if (e != cudaSuccess) return int(e);
+    const int64_t items = B * slices;
+    const unsigned grid = unsigned(items < int64_t(2 * sms) ? items : int64_t(2 * sms));
+    hsv_histogram_kernel<0><<<grid, kHsvThreads, sizeof(HsvSmem), st>>>(img, pixels, slices, vector_ok, items, out_counts);
   } else {
-    histogram_kernel<false><<<unsigned(B * slices), kHistThreads, 0, st>>>(img, pixels, slices, vector_ok, out_counts);
+    histogram_kernel<<<unsigned(B * slices), kHistThreads, 0, st>>>(img, pixels, slices, vector_ok, out_counts);
   }
   return int(cudaGetLastError());
 }
