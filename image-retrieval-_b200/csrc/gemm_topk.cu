@@ -1015,9 +1015,20 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
   for (int e = 0; e < E; ++e) r[e] = kKeyInf;
   int kept = 0;            // sorted survivors of earlier rounds occupy register positions [0, kept)
   int fill = 0;            // survivors staged in shared memory for the next round
+  constexpr int kAhead = 4;                                                // list chunks in flight per lane (the loop body
+  uint64_t ahead[kAhead];                                                  // branches into the sorter, so ptxas keeps one)
   for (int64_t base = 0; base < per_query; base += 32) {
-    const int64_t sidx = base + lane;
-    const uint64_t key = sidx < per_query ? src[sidx] : kKeyInf;
+    const int slot = int(base >> 5) % kAhead;
+    if (slot == 0) {
+#pragma unroll
+      for (int a = 0; a < kAhead; ++a) {
+        const int64_t sidx = base + 32 * a + lane;
+        ahead[a] = sidx < per_query ? src[sidx] : kKeyInf;
+      }
+    }
+    uint64_t key = ahead[0];
+#pragma unroll
+    for (int a = 1; a < kAhead; ++a) if (slot == a) key = ahead[a];
     const bool keep = key <= limit && key != kKeyInf;
     const uint32_t m = __ballot_sync(0xffffffffu, keep);
     if (keep) stage[fill + __popc(m & ((1u << lane) - 1))] = key;
@@ -1067,7 +1078,25 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
   const float qn = sqrtf(qss);
 
   const int nl = (kp + E - 1) / E;
+  // The candidates are visited one after the other (two 16-byte loads per lane and row, then a butterfly), i.e. one DRAM
+  // latency per candidate.  Lane L owns the E keys of step L: two steps ahead it asks the L2 for its E rows with one
+  // bulk prefetch each, so the visit finds them on chip (about 8 KB in flight per warp, 40 MB over the whole GPU).
+  const uint32_t row_bytes = uint32_t(D) * uint32_t(sizeof(T));
+  auto prefetch_rows = [&](int owner) {
+    if (rerank && lane == owner && owner < nl) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if (owner * E + e < kp && r[e] != kKeyInf) {
+          const T* xrow = X + int64_t(key_index(r[e])) * D;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(xrow), "r"(row_bytes) : "memory");
+        }
+      }
+    }
+  };
+  prefetch_rows(0);
+  prefetch_rows(1);
   for (int L = 0; L < nl; ++L) {
+    prefetch_rows(L + 2);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int c = L * E + e;
