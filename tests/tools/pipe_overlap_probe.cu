@@ -60,6 +60,9 @@ int main() {
   run<18>("8 IMAD + 8 PRMT", out, 16);
   run<17>("8 FFMA2 + 8 IMAD", out, 16);
   run<23>("8 FFMA2 + 8 IMAD + 8 PRMT + 8 FMNMX3", out, 32);
+  run<9>("8 FFMA2 + 8 FFMA", out, 16);
+  run<24>("8 FFMA + 8 IMAD", out, 16);
+  run<12>("8 FFMA + 8 FMNMX3", out, 16);
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
