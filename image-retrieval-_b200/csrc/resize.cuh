@@ -19,6 +19,10 @@ namespace b200ir {
 constexpr int kResizePrecisionBits = 32 - 8 - 2;
 constexpr int kResizeThreads = 256;
 constexpr int kRowBatch = 8;
+#ifndef RESIZE_RPB
+#define RESIZE_RPB 16
+#endif
+constexpr int kResizeRowsPerBlock = RESIZE_RPB;   // output rows per CTA (largest tried first)
 constexpr int kResizeSmemBudget = 160 * 1024;
 
 struct ResampleTable {
@@ -95,15 +99,17 @@ inline ResizePlan make_resize_plan(int H, int W, int rh, int rw, int top, int le
   p.row_buf_bytes = int(round_up64(int64_t(p.tx.in_hi - p.tx.in_lo) * 3 + 16 + 48, 16));   // +48: fixed-trip tap loops read past the span
   const int64_t out_row = int64_t(cw) * 3;
   // the largest group of output rows whose input-row window (tile) + row buffers fit the shared-memory budget
-  for (int rpb = 16; rpb >= 1; rpb >>= 1) {
+  for (int rpb = kResizeRowsPerBlock; rpb >= 1; rpb >>= 1) {
     int max_rows = 0;
     for (int y0 = 0; y0 < ch; y0 += rpb) {
       const int y1 = (y0 + rpb < ch ? y0 + rpb : ch) - 1;
       const int rows = p.ty.bounds[2 * y1] + p.ty.bounds[2 * y1 + 1] - p.ty.bounds[2 * y0];
       if (rows > max_rows) max_rows = rows;
     }
-    const size_t smem = size_t(kRowBatch) * p.row_buf_bytes + size_t(max_rows) * size_t(round_up64(out_row, 4)) +
-                        size_t(rpb) * (2 + p.ty.ksize) * 4;
+    // tile rows + 3: the 4-tap groups of the vertical pass read up to 3 rows past a window (against zero coefficients);
+    // vertical table per output row: first row, tap count, then 3 signed-byte limbs per group of 4 taps
+    const size_t smem = size_t(2 * kRowBatch) * p.row_buf_bytes + size_t(max_rows + 3) * size_t(round_up64(out_row, 4)) +
+                        size_t(rpb) * (2 + 3 * ((p.ty.ksize + 3) / 4)) * 4;
     if (smem <= size_t(kResizeSmemBudget)) {
       p.rows_per_block = rpb; p.max_rows = max_rows; p.smem_bytes = smem; p.ok = true;
       break;
@@ -131,15 +137,34 @@ __device__ __forceinline__ uint8_t clip8(int v) {
   return uint8_t(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
+// A 22-bit signed coefficient as three signed-byte limbs, k = l0 + 2^8 l1 + 2^16 l2 (balanced digits), so that four 8-bit
+// samples meet four taps in one dp4a per limb: sum(p k) = s0 + 2^8 s1 + 2^16 s2 exactly (every s fits 20 bits).
+__device__ __forceinline__ void coeff_limbs(int k, int& l0, int& l1, int& l2) {
+  l0 = ((k + 128) & 255) - 128;
+  const int k1 = (k - l0) >> 8;
+  l1 = ((k1 + 128) & 255) - 128;
+  l2 = (k1 - l1) >> 8;
+}
+__device__ __forceinline__ int dp4a_u8s8(uint32_t samples, int limbs, int acc) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(samples), "r"(limbs), "r"(acc));
+  return d;
+}
+__device__ __forceinline__ int pack_limb(int a, int b, int c, int d) {
+  return (a & 255) | ((b & 255) << 8) | ((c & 255) << 16) | ((d & 255) << 24);
+}
+
 // KREG > 0: horizontal taps of "this thread's" output column live in KREG registers (kx <= KREG, cw <= kResizeThreads;
 // table entries past the tap count are zero and the row buffers are padded, so the tap loop has a fixed trip count).
 // KREG == 0: any geometry, taps read through the read-only cache.
 template <int KREG>
 __global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs a) {
   extern __shared__ __align__(16) uint8_t rs_smem[];
-  uint8_t* rowbuf = rs_smem;                                     // kRowBatch x row_buf_bytes
-  uint8_t* tile = rs_smem + kRowBatch * a.row_buf_bytes;         // max_rows x tile_pitch (horizontally resampled rows)
-  int32_t* ksm = reinterpret_cast<int32_t*>(tile + a.max_rows * a.tile_pitch);   // rows_per_block x (2 + ky): vertical taps
+  uint8_t* rowbuf_base = rs_smem;                                // 2 x kRowBatch x row_buf_bytes (double-buffered)
+  uint8_t* tile = rs_smem + 2 * kRowBatch * a.row_buf_bytes;     // max_rows x tile_pitch (horizontally resampled rows)
+  const int kgy = (a.ky + 3) >> 2;                               // groups of four vertical taps
+  const int kstride = 2 + 3 * kgy;
+  int32_t* ksm = reinterpret_cast<int32_t*>(tile + (a.max_rows + 3) * a.tile_pitch);   // rows_per_block x (2 + 3 kgy): vertical limbs
   const int tid = threadIdx.x;
   const int y0 = blockIdx.x * a.rows_per_block;
   const int y1 = min(a.ch, y0 + a.rows_per_block);
@@ -150,22 +175,44 @@ __global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs 
   const int64_t seg_off = int64_t(a.x_lo) * 3;
   const int seg_bytes = (a.x_hi - a.x_lo) * 3;
 
-  for (int i = tid; i < (y1 - y0) * (2 + a.ky); i += kResizeThreads) {
-    const int yy = i / (2 + a.ky), j = i - yy * (2 + a.ky);
-    ksm[i] = j < 2 ? a.yb[2 * (y0 + yy) + j] : a.yk[(y0 + yy) * a.ky + j - 2];
+  for (int i = tid; i < (y1 - y0) * kstride; i += kResizeThreads) {
+    const int yy = i / kstride, j = i - yy * kstride;
+    if (j < 2) ksm[i] = a.yb[2 * (y0 + yy) + j];
+    else {
+      const int g = (j - 2) / 3, l = (j - 2) - 3 * g;
+      int lim[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int tap = 4 * g + t;
+        int l3[3];
+        coeff_limbs(tap < a.ky ? a.yk[(y0 + yy) * a.ky + tap] : 0, l3[0], l3[1], l3[2]);
+        lim[t] = l == 0 ? l3[0] : (l == 1 ? l3[1] : l3[2]);
+      }
+      ksm[i] = pack_limb(lim[0], lim[1], lim[2], lim[3]);
+    }
   }
-  int kreg[KREG > 0 ? KREG : 1];
+  constexpr int KG = KREG > 0 ? (KREG + 3) / 4 : 1;              // groups of four horizontal taps
+  int klim[KG][3];                                               // limbs of "this thread's" taps, four taps per register
   int my_off = 0;
   if (KREG > 0 && tid < a.cw) {
 #pragma unroll
-    for (int j = 0; j < KREG; ++j) kreg[j] = j < a.kx ? a.xk[tid * a.kx + j] : 0;
+    for (int g = 0; g < KG; ++g) {
+      int l0[4], l1[4], l2[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) coeff_limbs(4 * g + t < a.kx ? a.xk[tid * a.kx + 4 * g + t] : 0, l0[t], l1[t], l2[t]);
+      klim[g][0] = pack_limb(l0[0], l0[1], l0[2], l0[3]);
+      klim[g][1] = pack_limb(l1[0], l1[1], l1[2], l1[3]);
+      klim[g][2] = pack_limb(l2[0], l2[1], l2[2], l2[3]);
+    }
     my_off = (a.xb[2 * tid] - a.x_lo) * 3;
   }
 
-  for (int rb = r0; rb < r1; rb += kRowBatch) {
+  // Input rows reach shared memory by cp.async, one batch ahead: batch i + 1 is in flight while batch i is resampled
+  // (one barrier per batch; the single-buffer version waited for every batch's loads with nothing else to do).
+  auto stage_rows = [&](int rb, uint8_t* rowbuf) {
     const int nrows = min(kRowBatch, r1 - rb);
-    // stage the needed byte span of up to kRowBatch input rows, one warp per row; 16-byte loads from the aligned
-    // address below the span
+    // the needed byte span of up to kRowBatch input rows, one warp per row; 16-byte copies from the aligned address
+    // below the span
     for (int r = tid >> 5; r < nrows; r += kResizeThreads / 32) {
       const uint8_t* src = img + (int64_t(rb + r) * a.W) * 3 + seg_off;
       const int mis = int(reinterpret_cast<uintptr_t>(src) & 15);
@@ -176,7 +223,8 @@ __global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs 
       // final image, which is read bytewise
       const bool tail_safe = rb + r + 1 < a.H || blockIdx.y + 1 < gridDim.y;
       const int n_fast = tail_safe ? n16 : n16 - 1;
-      for (int i = tid & 31; i < n_fast; i += 32) dst16[i] = __ldg(src16 + i);
+      for (int i = tid & 31; i < n_fast; i += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(uint32_t(__cvta_generic_to_shared(dst16 + i))), "l"(src16 + i) : "memory");
       if (!tail_safe && (tid & 31) == 0) {
         uint8_t* d = reinterpret_cast<uint8_t*>(dst16 + n_fast);
         const uint8_t* s = reinterpret_cast<const uint8_t*>(src16 + n_fast);
@@ -184,7 +232,16 @@ __global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs 
         for (int b = 0; b < 16; ++b) d[b] = b < valid ? s[b] : 0;
       }
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_rows(r0, rowbuf_base);
+  int parity = 0;
+  for (int rb = r0; rb < r1; rb += kRowBatch, parity ^= 1) {
+    const int nrows = min(kRowBatch, r1 - rb);
+    uint8_t* rowbuf = rowbuf_base + parity * kRowBatch * a.row_buf_bytes;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                             // batch `rb` has landed; everybody is done with the other buffer
+    if (rb + kRowBatch < r1) stage_rows(rb + kRowBatch, rowbuf_base + (parity ^ 1) * kRowBatch * a.row_buf_bytes);
     if (KREG > 0) {
       if (tid < a.cw) {
         for (int r = 0; r < nrows; ++r) {
@@ -194,19 +251,29 @@ __global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs 
           const int off = int(reinterpret_cast<uintptr_t>(src) & 15) + my_off;
           const uint32_t* pw = reinterpret_cast<const uint32_t*>(rowbuf + r * a.row_buf_bytes + (off & ~3));
           const uint32_t sel = 0x3210u + 0x1111u * uint32_t(off & 3);
-          constexpr int NW = (3 * KREG + 3) / 4;
+          constexpr int NW = 3 * KG;                               // 12 bytes = 4 taps x 3 channels per group
           uint32_t w[NW + 1];
 #pragma unroll
           for (int i = 0; i <= NW; ++i) w[i] = pw[i];
 #pragma unroll
           for (int i = 0; i < NW; ++i) w[i] = __byte_perm(w[i], w[i + 1], sel);
-          int acc0 = 1 << (kResizePrecisionBits - 1), acc1 = acc0, acc2 = acc0;
+          // per group and channel: gather the channel's four samples (two PRMTs), then one dp4a per coefficient limb
+          // (round 1: one PRMT + one IMAD per sample and tap; taps past kx and bytes past the window meet zero limbs)
+          int s0[3] = {0, 0, 0}, s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
 #pragma unroll
-          for (int j = 0; j < KREG; ++j) {
-            acc0 += int(__byte_perm(w[(3 * j) >> 2], 0, 0x4440u + ((3 * j) & 3))) * kreg[j];
-            acc1 += int(__byte_perm(w[(3 * j + 1) >> 2], 0, 0x4440u + ((3 * j + 1) & 3))) * kreg[j];
-            acc2 += int(__byte_perm(w[(3 * j + 2) >> 2], 0, 0x4440u + ((3 * j + 2) & 3))) * kreg[j];
+          for (int g = 0; g < KG; ++g) {
+            const uint32_t w0 = w[3 * g], w1 = w[3 * g + 1], w2 = w[3 * g + 2];
+            const uint32_t c0 = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);     // bytes 0, 3, 6, 9
+            const uint32_t c1 = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);     // bytes 1, 4, 7, 10
+            const uint32_t c2 = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);     // bytes 2, 5, 8, 11
+            s0[0] = dp4a_u8s8(c0, klim[g][0], s0[0]); s1[0] = dp4a_u8s8(c0, klim[g][1], s1[0]); s2[0] = dp4a_u8s8(c0, klim[g][2], s2[0]);
+            s0[1] = dp4a_u8s8(c1, klim[g][0], s0[1]); s1[1] = dp4a_u8s8(c1, klim[g][1], s1[1]); s2[1] = dp4a_u8s8(c1, klim[g][2], s2[1]);
+            s0[2] = dp4a_u8s8(c2, klim[g][0], s0[2]); s1[2] = dp4a_u8s8(c2, klim[g][1], s1[2]); s2[2] = dp4a_u8s8(c2, klim[g][2], s2[2]);
           }
+          const int half = 1 << (kResizePrecisionBits - 1);
+          const int acc0 = half + s0[0] + (s1[0] << 8) + (s2[0] << 16);
+          const int acc1 = half + s0[1] + (s1[1] << 8) + (s2[1] << 16);
+          const int acc2 = half + s0[2] + (s1[2] << 8) + (s2[2] << 16);
           uint8_t* t = tile + (rb - r0 + r) * a.tile_pitch + tid * 3;
           t[0] = clip8(acc0); t[1] = clip8(acc1); t[2] = clip8(acc2);
         }
@@ -230,8 +297,8 @@ __global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs 
         t[0] = clip8(acc0); t[1] = clip8(acc1); t[2] = clip8(acc2);
       }
     }
-    __syncthreads();
   }
+  __syncthreads();                                               // the tile is complete
   // vertical pass out of the tile: one thread = 4 consecutive bytes of an output row, taps broadcast from shared memory
   uint8_t* out = a.out + (int64_t(blockIdx.y) * a.ch + y0) * out_row;
   if (a.word_out) {
@@ -239,31 +306,40 @@ __global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs 
     const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
     for (int wd = tid; wd < words; wd += kResizeThreads) {
       for (int yy = 0; yy < y1 - y0; ++yy) {
-        const int32_t* k = ksm + yy * (2 + a.ky);
+        const int32_t* k = ksm + yy * kstride;
         const int n = k[1];
         const uint32_t* px = tile32 + (k[0] - r0) * pitch4 + wd;
-        int acc0 = 1 << (kResizePrecisionBits - 1), acc1 = acc0, acc2 = acc0, acc3 = acc0;
-#pragma unroll 4
-        for (int j = 0; j < n; ++j) {
-          const uint32_t w = px[j * pitch4];
-          const int kj = k[2 + j];
-          acc0 += int(__byte_perm(w, 0, 0x4440u)) * kj;
-          acc1 += int(__byte_perm(w, 0, 0x4441u)) * kj;
-          acc2 += int(__byte_perm(w, 0, 0x4442u)) * kj;
-          acc3 += int(w >> 24) * kj;
+        int s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+        for (int g = 0; 4 * g < n; ++g) {
+          // four rows x four columns: transpose (8 PRMTs) so that each column's four samples share a register
+          const uint32_t r0w = px[(4 * g) * pitch4], r1w = px[(4 * g + 1) * pitch4], r2w = px[(4 * g + 2) * pitch4],
+                         r3w = px[(4 * g + 3) * pitch4];
+          const uint32_t t0 = __byte_perm(r0w, r1w, 0x5140), t1 = __byte_perm(r2w, r3w, 0x5140);
+          const uint32_t t2 = __byte_perm(r0w, r1w, 0x7362), t3 = __byte_perm(r2w, r3w, 0x7362);
+          const uint32_t col[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632), __byte_perm(t2, t3, 0x5410),
+                                   __byte_perm(t2, t3, 0x7632)};
+          const int l0 = k[2 + 3 * g], l1 = k[3 + 3 * g], l2 = k[4 + 3 * g];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            s0[c] = dp4a_u8s8(col[c], l0, s0[c]); s1[c] = dp4a_u8s8(col[c], l1, s1[c]); s2[c] = dp4a_u8s8(col[c], l2, s2[c]);
+          }
         }
-        reinterpret_cast<uint32_t*>(out)[yy * words + wd] = uint32_t(clip8(acc0)) | (uint32_t(clip8(acc1)) << 8) |
-                                                             (uint32_t(clip8(acc2)) << 16) | (uint32_t(clip8(acc3)) << 24);
+        const int half = 1 << (kResizePrecisionBits - 1);
+        uint32_t outw = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) outw |= uint32_t(clip8(half + s0[c] + (s1[c] << 8) + (s2[c] << 16))) << (8 * c);
+        reinterpret_cast<uint32_t*>(out)[yy * words + wd] = outw;
       }
     }
   } else {
     for (int o = tid; o < (y1 - y0) * out_row; o += kResizeThreads) {
       const int yy = o / out_row, e = o - yy * out_row;
-      const int32_t* k = ksm + yy * (2 + a.ky);
+      const int32_t* k = ksm + yy * kstride;
       const int n = k[1];
       const uint8_t* px = tile + (k[0] - r0) * a.tile_pitch + e;
+      const int32_t* kt = a.yk + (y0 + yy) * a.ky;
       int acc = 1 << (kResizePrecisionBits - 1);
-      for (int j = 0; j < n; ++j) acc += int(px[j * a.tile_pitch]) * k[2 + j];
+      for (int j = 0; j < n; ++j) acc += int(px[j * a.tile_pitch]) * __ldg(kt + j);
       out[o] = clip8(acc);
     }
   }
