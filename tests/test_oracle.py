@@ -127,6 +127,44 @@ def test_hsv_restatement_all_colours():
     assert np.array_equal(H.rgb_to_hsv_u8(rgb), ref)
 
 
+def test_hsv_fp32_construction_all_colours():
+    """The device kernel (csrc/histogram.cuh, hsv_histogram_kernel) does OpenCV's fixed-point conversion with fp32 operations on
+    exact integers: 2^23-biased bytes, one exact fma for d*sdiv + 2^11 / hnum*hdiv + 2^11, floor by fma.rm against 2^23, the
+    hue numerator as a penalised 3-input min, slots 6..14 folded onto 8 hue bins.  Restated here operation by operation
+    in float64 (every intermediate is checked to be exactly representable in fp32, so the fp32 kernel computes the same
+    numbers) and compared with the integer oracle on all 2^24 colours."""
+    M = 2.0 ** 23
+    cc = 2913.0 / 65536.0
+    kh = M - M * cc
+    assert kh == float(np.float32(kh)) and M * cc == 372864.0
+
+    def exact32(x):
+        assert np.array_equal(x.astype(np.float32).astype(np.float64), x)
+        return x
+
+    for r0 in range(0, 256, 16):
+        c = np.arange(r0 << 16, (r0 + 16) << 16, dtype=np.uint32)
+        r = ((c >> 16) & 255).astype(np.float64) + M
+        g = ((c >> 8) & 255).astype(np.float64) + M
+        b = (c & 255).astype(np.float64) + M
+        v = np.maximum(np.maximum(r, g), b)
+        d = v - np.minimum(np.minimum(r, g), b)
+        sd = H.SDIV[(v - M).astype(np.int64)].astype(np.float64)
+        hd = H.HDIV[d.astype(np.int64)].astype(np.float64)
+        s1 = np.floor(exact32(d * sd + 2048.0) * 2.0 ** -17 + M)                   # fma.rn, then fma.rm
+        v1 = np.floor(v * 2.0 ** -5 + (M - 2.0 ** 18))
+        cb = exact32(4 * d + exact32(r - g))
+        cg = exact32(2048.0 * exact32(v - g) + exact32(2 * d + exact32(b - r)))
+        cr = exact32(2048.0 * exact32(v - r) + exact32(g - b))
+        hn = np.minimum(np.minimum(cr, cg), cb)
+        u1 = np.floor(exact32(hn * hd + 2048.0) * 2.0 ** -12 + (M + 180.0))
+        h1 = np.floor(u1 * cc + kh)
+        slot, sb, vb = (h1 - M).astype(np.int64), (s1 - M).astype(np.int64), (v1 - M).astype(np.int64)
+        assert slot.min() >= 6 and slot.max() <= 14
+        img = np.stack([(c >> 16) & 255, (c >> 8) & 255, c & 255], axis=1).astype(np.uint8)
+        assert np.array_equal((slot & 7) * 64 + sb * 8 + vb, H.bin_index(img, "hsv"))
+
+
 def test_histogram_vs_opencv(golden_dir):
     g = np.load(os.path.join(golden_dir, "hist_golden.npz"))
     imgs = g["images"]
