@@ -244,11 +244,10 @@ __global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs 
     if (rb + kRowBatch < r1) stage_rows(rb + kRowBatch, rowbuf_base + (parity ^ 1) * kRowBatch * a.row_buf_bytes);
     if (KREG > 0) {
       if (tid < a.cw) {
-        for (int r = 0; r < nrows; ++r) {
-          const uint8_t* src = img + (int64_t(rb + r) * a.W) * 3 + seg_off;
-          // the 3*KREG bytes of this pixel's window: aligned 32-bit shared loads, re-aligned with one PRMT per word
+        // one input row of "this thread's" output column; `off` = byte offset of its window in the staged row
+        auto hrow = [&](int r, int off) {
+          // the 12 KG bytes of this pixel's window: aligned 32-bit shared loads, re-aligned with one PRMT per word
           // (byte loads would make the kernel LSU-bound: 3 shared loads per tap)
-          const int off = int(reinterpret_cast<uintptr_t>(src) & 15) + my_off;
           const uint32_t* pw = reinterpret_cast<const uint32_t*>(rowbuf + r * a.row_buf_bytes + (off & ~3));
           const uint32_t sel = 0x3210u + 0x1111u * uint32_t(off & 3);
           constexpr int NW = 3 * KG;                               // 12 bytes = 4 taps x 3 channels per group
@@ -259,7 +258,8 @@ __global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs 
           for (int i = 0; i < NW; ++i) w[i] = __byte_perm(w[i], w[i + 1], sel);
           // per group and channel: gather the channel's four samples (two PRMTs), then one dp4a per coefficient limb
           // (round 1: one PRMT + one IMAD per sample and tap; taps past kx and bytes past the window meet zero limbs)
-          int s0[3] = {0, 0, 0}, s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
+          const int half = 1 << (kResizePrecisionBits - 1);
+          int s0[3] = {half, half, half}, s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
 #pragma unroll
           for (int g = 0; g < KG; ++g) {
             const uint32_t w0 = w[3 * g], w1 = w[3 * g + 1], w2 = w[3 * g + 2];
@@ -270,12 +270,24 @@ __global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs 
             s0[1] = dp4a_u8s8(c1, klim[g][0], s0[1]); s1[1] = dp4a_u8s8(c1, klim[g][1], s1[1]); s2[1] = dp4a_u8s8(c1, klim[g][2], s2[1]);
             s0[2] = dp4a_u8s8(c2, klim[g][0], s0[2]); s1[2] = dp4a_u8s8(c2, klim[g][1], s1[2]); s2[2] = dp4a_u8s8(c2, klim[g][2], s2[2]);
           }
-          const int half = 1 << (kResizePrecisionBits - 1);
-          const int acc0 = half + s0[0] + (s1[0] << 8) + (s2[0] << 16);
-          const int acc1 = half + s0[1] + (s1[1] << 8) + (s2[1] << 16);
-          const int acc2 = half + s0[2] + (s1[2] << 8) + (s2[2] << 16);
+          const int acc0 = s0[0] + (s1[0] << 8) + (s2[0] << 16);
+          const int acc1 = s0[1] + (s1[1] << 8) + (s2[1] << 16);
+          const int acc2 = s0[2] + (s1[2] << 8) + (s2[2] << 16);
           uint8_t* t = tile + (rb - r0 + r) * a.tile_pitch + tid * 3;
           t[0] = clip8(acc0); t[1] = clip8(acc1); t[2] = clip8(acc2);
+        };
+        if (((a.W * 3) & 15) == 0) {
+          // the row pitch is a multiple of 16 bytes (every width that is a multiple of 16 pixels): the staging misalignment
+          // and with it the window offset / PRMT selector are the same for every row - computed once, two rows per trip
+          const int off = int((reinterpret_cast<uintptr_t>(img) + uintptr_t(seg_off)) & 15) + my_off;
+          int r = 0;
+          for (; r + 1 < nrows; r += 2) { hrow(r, off); hrow(r + 1, off); }
+          if (r < nrows) hrow(r, off);
+        } else {
+          for (int r = 0; r < nrows; ++r) {
+            const uint8_t* src = img + (int64_t(rb + r) * a.W) * 3 + seg_off;
+            hrow(r, int(reinterpret_cast<uintptr_t>(src) & 15) + my_off);
+          }
         }
       }
     } else {
@@ -304,8 +316,12 @@ __global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs 
   if (a.word_out) {
     const int words = out_row >> 2, pitch4 = a.tile_pitch >> 2;
     const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
-    for (int wd = tid; wd < words; wd += kResizeThreads) {
-      for (int yy = 0; yy < y1 - y0; ++yy) {
+    // work items (output row yy, word wd) dealt round-robin over all 256 threads: a 224-pixel row has 168 words, so one
+    // thread per word would leave a third of the CTA idle for the whole pass.  (wd, yy) advance without a division.
+    const int step_y = kResizeThreads / words, step_w = kResizeThreads - step_y * words;
+    int wd = tid % words, yy = tid / words;
+    for (; yy < y1 - y0; ) {
+      {
         const int32_t* k = ksm + yy * kstride;
         const int n = k[1];
         const uint32_t* px = tile32 + (k[0] - r0) * pitch4 + wd;
@@ -330,6 +346,8 @@ __global__ void __launch_bounds__(kResizeThreads) resize_crop_kernel(ResizeArgs 
         for (int c = 0; c < 4; ++c) outw |= uint32_t(clip8(half + s0[c] + (s1[c] << 8) + (s2[c] << 16))) << (8 * c);
         reinterpret_cast<uint32_t*>(out)[yy * words + wd] = outw;
       }
+      wd += step_w; yy += step_y;
+      if (wd >= words) { wd -= words; ++yy; }
     }
   } else {
     for (int o = tid; o < (y1 - y0) * out_row; o += kResizeThreads) {
