@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "gemm_topk.h"
 #include "scan_plan.h"
@@ -993,6 +994,33 @@ index_rows_kernel(const T* __restrict__ X, int64_t N, int64_t N_pad, int D, floa
   }
 }
 
+// The same 8 elements from a row staged in shared memory (re-rank ring of gemm_finalize_kernel)
+template <typename T> __device__ __forceinline__ void load8s(const T* p, float (&f)[8]);
+template <> __device__ __forceinline__ void load8s<float>(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8s<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 w = *reinterpret_cast<const uint4*>(p);
+  f[0] = bf16_lo(w.x); f[1] = bf16_hi(w.x); f[2] = bf16_lo(w.y); f[3] = bf16_hi(w.y);
+  f[4] = bf16_lo(w.z); f[5] = bf16_hi(w.z); f[6] = bf16_lo(w.w); f[7] = bf16_hi(w.w);
+}
+
+// Re-rank ring of gemm_finalize_kernel: every warp owns FIN_RING_KB KB of shared memory (at least two rows) into which
+// the candidate rows arrive by cp.async.bulk, one mbarrier per slot.  Measured on the headline (10k x 1M x 512 bf16,
+// k' = 107, same-box A/B of the re-rank kernel): 16 KB 0.61 ms, 8 KB 0.50 ms, 4 KB 0.45 ms, 2 KB 0.45 ms against 0.57 ms
+// for the lane loads behind an L2 prefetch (-DFIN_RING_KB=0 still builds that path): resident warps (8 CTAs per SM at
+// 64 registers and <= 25 KB) matter more than rows in flight, so the ring is kept shallow.
+#ifndef FIN_RING_KB
+#define FIN_RING_KB 4
+#endif
+template <typename T, int QJ> struct FinRing {
+  static constexpr int kSlotBytes = QJ * 256 * int(sizeof(T));            // widest row of the instantiation
+  static constexpr int kWant = FIN_RING_KB * 1024;
+  static constexpr int kBytes = kWant >= 2 * kSlotBytes ? kWant : 2 * kSlotBytes;
+  static constexpr int kSlots = kBytes / kSlotBytes > 16 ? 16 : kBytes / kSlotBytes;   // a power of two, 2..16
+};
+
 // A-posteriori exactness certificate (see gemm_finalize_kernel) and the list of queries that failed it
 struct Certify {
   float u_eff;                 // |computed dot - exact dot| <= u_eff * |q| * |x| on the tensor-core pass
@@ -1028,6 +1056,21 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
   const uint64_t limit = (uint64_t(thr_g[q]) << 32) | 0xffffffffull;       // 0xffffffff.. = none published: keep all
   __shared__ uint64_t stage_s[4][32 * E];
   uint64_t* stage = stage_s[threadIdx.x >> 5];
+#if FIN_RING_KB > 0
+  using Ring = FinRing<T, QJ>;
+  constexpr int NS = Ring::kSlots;
+  extern __shared__ __align__(128) unsigned char ring_s[];
+  __shared__ __align__(8) uint64_t ring_bar_s[4][16];
+  const unsigned char* ring = ring_s + (threadIdx.x >> 5) * Ring::kBytes;
+  const uint32_t ring_a = smem_u32(ring);
+  const uint32_t bar_a = smem_u32(&ring_bar_s[threadIdx.x >> 5][0]);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) mbar_init(bar_a + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+#endif
   uint64_t r[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) r[e] = kKeyInf;
@@ -1102,6 +1145,25 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
   // prefetched rows were evicted again before their visit (ncu: 1.13 -> 1.70 GB of DRAM reads); the partition lists are
   // read with the streaming hint for the same reason.
   const uint32_t row_bytes = uint32_t(D) * uint32_t(sizeof(T));
+#if FIN_RING_KB > 0
+  // The rows come through a per-warp shared-memory ring: the lane that owns candidate c asks for its row with ONE
+  // cp.async.bulk (global -> slot c % NS, completing on that slot's mbarrier) NS candidates before the visit; the visit
+  // waits on the barrier and reads the row with 16-byte LDS in the same lane <-> element layout as the lane loads did
+  // (same sums in the same order: bit-identical results).  No load holds registers while it is in flight (64 instead
+  // of 72 registers: one more resident CTA) and every row crosses DRAM -> SM once (the L2 prefetch of the earlier path
+  // fetched a third of them twice).
+  auto issue_row = [&](uint64_t key, int c) {                    // owner lane only
+    const int s = c & (NS - 1);
+    mbar_expect_tx(bar_a + 8 * s, row_bytes);
+    bulk_load_1d(ring_a + uint32_t(s) * uint32_t(Ring::kSlotBytes), X + int64_t(key_index(key)) * D, row_bytes, bar_a + 8 * s);
+  };
+  if (rerank) {
+#pragma unroll
+    for (int c0 = 0; c0 < NS; ++c0)
+      if (lane == c0 / E && c0 < kp && r[c0 % E] != kKeyInf) issue_row(r[c0 % E], c0);
+  }
+  auto prefetch_rows = [&](int) {};
+#else
   auto prefetch_rows = [&](int owner) {
     if (rerank && lane == owner && owner < nl) {
 #pragma unroll
@@ -1113,6 +1175,7 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
       }
     }
   };
+#endif
   prefetch_rows(0);
   for (int L = 0; L < nl; ++L) {
     prefetch_rows(L + 1);
@@ -1124,14 +1187,23 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
       const uint32_t idx = key_index(key);
       float rank;
       if (rerank) {
+#if FIN_RING_KB > 0
+        mbar_wait(bar_a + 8 * (c & (NS - 1)), uint32_t(c / NS) & 1u);
+        const T* xrow = reinterpret_cast<const T*>(ring + (c & (NS - 1)) * Ring::kSlotBytes);
+#else
         const T* xrow = X + int64_t(idx) * D;
+#endif
         float dot = 0.f, xss = 0.f, d2 = 0.f;
 #pragma unroll
         for (int j = 0; j < QJ; ++j) {
           const int d = (lane + 32 * j) * 8;
           if (d < D) {
             float xf[8];
+#if FIN_RING_KB > 0
+            load8s<T>(xrow + d, xf);
+#else
             load8<T>(xrow + d, xf);
+#endif
             if (mode == MODE_L2) {                                 // warp-uniform: only the sums the metric needs
 #pragma unroll
               for (int t = 0; t < 8; ++t) { const float df = qf[j][t] - xf[t]; d2 = fmaf(df, df, d2); }
@@ -1151,6 +1223,13 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
             xss += __shfl_xor_sync(0xffffffffu, xss, o);
           }
         }
+#if FIN_RING_KB > 0
+        {   // every lane's reads of the slot fed the butterfly above: the slot takes candidate c + NS
+          __syncwarp();
+          const uint64_t k2 = r[(e + NS) % E];
+          if (lane == L + (e + NS) / E && c + NS < kp && k2 != kKeyInf) issue_row(k2, c + NS);
+        }
+#endif
         if (mode == MODE_L2) rank = d2;
         else {
           const float xn = sqrtf(xss);
@@ -1504,10 +1583,16 @@ int run_gemm_topk(int metric, int dtype, const void* Q, int64_t nq, const void* 
     // analysis; tests/test_gpu_tensor_fp32.py measures the actual worst error against them.
     Certify cert{f32 ? 6.1035156e-5f : 1.5258789e-5f, reinterpret_cast<const unsigned int*>(index + IL.off_max),
                  rerank ? fb_count : nullptr, fb_list};
-    auto fin = [&](auto kern, auto Qp, auto Xp) {
-      kern<<<blocks, 128, 0, st>>>(a.partial, a.thr_g, Qp, Xp, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, cert, out_score, out_idx);
-    };
     const bool wide = D > 512, big = pl.kp > 128;
+    auto fin = [&](auto kern, auto Qp, auto Xp) {
+      size_t ring_bytes = 0;
+#if FIN_RING_KB > 0
+      using TT = std::remove_cv_t<std::remove_pointer_t<decltype(Qp)>>;
+      ring_bytes = 4 * size_t(wide ? FinRing<TT, 8>::kBytes : FinRing<TT, 2>::kBytes);
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ring_bytes));   // per device: set on every call
+#endif
+      kern<<<blocks, 128, ring_bytes, st>>>(a.partial, a.thr_g, Qp, Xp, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, cert, out_score, out_idx);
+    };
     if (f32) {
       const float* Qp = static_cast<const float*>(Q);
       const float* Xp = static_cast<const float*>(X);

@@ -22,6 +22,13 @@ def ops():
     return o
 
 
+def _oracle_rows(nq, N, D, budget=2.5e9):
+    """Query rows to hold against the fp64 oracle: all of them, or an evenly spaced subset when the oracle's elementwise
+    L2 over nq x N x D would take most of a minute on the host (the GPU result is still computed for every query)."""
+    step = max(1, int(np.ceil(nq * N * D / budget)))
+    return np.arange(0, nq, step)
+
+
 def _tol(metric):
     if metric in ("cosine_similarity", "cosine_distance"):
         return dict(rtol=1e-5, atol=2e-6)
@@ -40,9 +47,10 @@ def test_fp32_tensor_path_vs_oracle(ops, metric, nq, N, D, k):
     X[11] = Q[3]                               # exact self match
     s, i = ops.topk(Q, X, metric, k)
     assert ops.last_fallback_count() is not None, "fp32 store did not take the tensor-core path"
-    truth = OM.pairwise_f64(Q, X, metric)
-    disputed = check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, k, OM.DESCENDING[metric], **_tol(metric))
-    assert disputed <= max(1, nq * k // 200), f"{disputed} disputed ranks"
+    rows = _oracle_rows(nq, N, D)
+    truth = OM.pairwise_f64(Q[rows], X, metric)
+    disputed = check_topk(s.cpu().numpy()[rows], i.cpu().numpy()[rows], truth, k, OM.DESCENDING[metric], **_tol(metric))
+    assert disputed <= max(1, len(rows) * k // 200), f"{disputed} disputed ranks"
     assert i[3, 0].item() == 11
 
 
@@ -152,7 +160,7 @@ def test_histogram_embeddings_fp32_l2_exact_indices(ops):
 
 
 def test_full_size_fp32_tensor_path(ops):
-    """north_star size for fp32 stores: 10k queries x 1M x 512 fp32, cosine and L2 top-100 on tcgen05; a 24-query
+    """north_star size for fp32 stores: 10k queries x 1M x 512 fp32, cosine and L2 top-100 on tcgen05; a 10-query
     sample is checked against the fp64 oracle, the whole batch through size-independent properties."""
     import torch
     dev = torch.device("cuda")
@@ -166,7 +174,7 @@ def test_full_size_fp32_tensor_path(ops):
     X[123_456] = Q[17]
     idx = ops.prepare_index(X)
     Xh = X.cpu().numpy()
-    sample = np.arange(0, nq, nq // 24)[:24]
+    sample = np.arange(0, nq, nq // 10)[:10]
     for metric in ("cosine_similarity", "l2"):
         s, i = ops.topk(Q, idx, metric, k)
         fb = ops.last_fallback_count()
@@ -200,9 +208,10 @@ def test_wide_rows_streamed_tensor_path(ops, bf16, nq, N, D, k):
     for metric in ("cosine_similarity", "l2"):
         s, i = ops.topk(Qd, Xd, metric, k)
         assert ops.last_fallback_count() is not None, "wide rows did not take the tensor-core path"
-        truth = OM.pairwise_f64(Q, X, metric)
-        disputed = check_topk(s.cpu().numpy(), i.cpu().numpy(), truth, k, OM.DESCENDING[metric], **_tol(metric))
-        assert disputed <= max(1, nq * k // 200), f"{disputed} disputed ranks"
+        rows = _oracle_rows(nq, N, D)
+        truth = OM.pairwise_f64(Q[rows], X, metric)
+        disputed = check_topk(s.cpu().numpy()[rows], i.cpu().numpy()[rows], truth, k, OM.DESCENDING[metric], **_tol(metric))
+        assert disputed <= max(1, len(rows) * k // 200), f"{disputed} disputed ranks"
         assert i[2, 0].item() == 9
 
 
