@@ -1138,32 +1138,104 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
   for (int o = 16; o > 0; o >>= 1) qss += __shfl_xor_sync(0xffffffffu, qss, o);
   const float qn = sqrtf(qss);
 
-  const int nl = (kp + E - 1) / E;
+  const uint32_t row_bytes = uint32_t(D) * uint32_t(sizeof(T));
+  // exact rank value of one candidate from its row (global memory, or a ring slot in shared memory): direct fp32 sums,
+  // lane <-> element layout and butterfly identical in both builds, so the results are bit-identical
+  auto exact_rank = [&](const T* xrow, auto in_smem, auto&& after_reads) -> float {
+    float dot = 0.f, xss = 0.f, d2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < QJ; ++j) {
+      const int d = (lane + 32 * j) * 8;
+      if (d < D) {
+        float xf[8];
+        if constexpr (decltype(in_smem)::value) load8s<T>(xrow + d, xf); else load8<T>(xrow + d, xf);
+        if (mode == MODE_L2) {                                     // warp-uniform: only the sums the metric needs
+#pragma unroll
+          for (int t = 0; t < 8; ++t) { const float df = qf[j][t] - xf[t]; d2 = fmaf(df, df, d2); }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) { dot = fmaf(xf[t], qf[j][t], dot); xss = fmaf(xf[t], xf[t], xss); }
+        }
+      }
+    }
+    if (mode == MODE_L2) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    } else {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        xss += __shfl_xor_sync(0xffffffffu, xss, o);
+      }
+    }
+    after_reads();
+    if (mode == MODE_L2) return d2;
+    const float xn = sqrtf(xss);
+    float cs = (qn != 0.f && xn != 0.f) ? dot / (qn * xn) : 0.f;
+    if (mode == MODE_ABSCOS) cs = fabsf(cs);
+    return -cs;
+  };
+  auto epilogue_rank = [&](uint64_t key) -> float {               // no re-rank: the epilogue-domain score
+    const float v = -key_rank(key);
+    if (mode == MODE_L2) return fmaxf(qss - v, 0.f);               // |q|^2 + |x|^2 - 2 q.x
+    return -(v * (qn != 0.f ? 1.0f / qn : 0.f));
+  };
+#if FIN_RING_KB > 0
+  // The sorted candidates move to this warp's staging buffer (candidate c at (c % E) * 32 + c / E: conflict-free for the
+  // lane-major copy in and out) and are visited by a ROLLED loop: with the keys in registers the loop had to be unrolled
+  // E times (static register indices), ~1500 instructions that 32 resident warps walk at different places - ncu's top
+  // stall reason of that build was `no_instruction` (instruction fetch), 3.4 of 10.7 stall cycles per issue.
+  // The rows come through a per-warp shared-memory ring: lane 0 asks for the row of candidate c with ONE cp.async.bulk
+  // (global -> slot c % NS, completing on that slot's mbarrier) NS candidates before the visit; the visit waits on the
+  // barrier and reads the row with 16-byte LDS.  No load holds registers while it is in flight (64 registers: 8 CTAs
+  // per SM) and every row crosses DRAM -> SM once (the L2 prefetch of the earlier path fetched a third of them twice).
+  auto pos = [](int c) { return (c % E) * 32 + c / E; };
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < E; ++e) stage[e * 32 + lane] = r[e];
+  __syncwarp();
+  auto issue_row = [&](int c) {                                    // lane 0 only
+    if (c < kp) {
+      const uint64_t key = stage[pos(c)];
+      if (key != kKeyInf) {
+        const int s = c & (NS - 1);
+        mbar_expect_tx(bar_a + 8 * s, row_bytes);
+        bulk_load_1d(ring_a + uint32_t(s) * uint32_t(Ring::kSlotBytes), X + int64_t(key_index(key)) * D, row_bytes, bar_a + 8 * s);
+      }
+    }
+  };
+  if (rerank && lane == 0) {
+#pragma unroll
+    for (int c0 = 0; c0 < NS; ++c0) issue_row(c0);
+  }
+#pragma unroll 1
+  for (int c = 0; c < kp; ++c) {
+    const uint64_t key = stage[pos(c)];
+    if (key == kKeyInf) break;                                     // sorted: nothing valid follows (warp-uniform)
+    float rank;
+    if (rerank) {
+      mbar_wait(bar_a + 8 * (c & (NS - 1)), uint32_t(c / NS) & 1u);
+      const T* xrow = reinterpret_cast<const T*>(ring + (c & (NS - 1)) * Ring::kSlotBytes);
+      rank = exact_rank(xrow, std::true_type{}, [&] {
+        __syncwarp();                                              // every lane's reads of the slot fed the butterfly:
+        if (lane == 0) issue_row(c + NS);                          // the slot takes candidate c + NS
+      });
+    } else {
+      rank = epilogue_rank(key);
+    }
+    __syncwarp();
+    if (lane == 0) stage[pos(c)] = make_key(rank, key_index(key));
+  }
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < E; ++e) r[e] = stage[e * 32 + lane];
+#else
   // The candidates are visited one after the other (two 16-byte loads per lane and row, then a butterfly), i.e. one DRAM
   // latency per candidate.  Lane L owns the E keys of step L: one step ahead it asks the L2 for its E rows with one bulk
   // prefetch each, so the visit finds them on chip.  One step, not two: with 16 rows per warp in flight a third of the
   // prefetched rows were evicted again before their visit (ncu: 1.13 -> 1.70 GB of DRAM reads); the partition lists are
   // read with the streaming hint for the same reason.
-  const uint32_t row_bytes = uint32_t(D) * uint32_t(sizeof(T));
-#if FIN_RING_KB > 0
-  // The rows come through a per-warp shared-memory ring: the lane that owns candidate c asks for its row with ONE
-  // cp.async.bulk (global -> slot c % NS, completing on that slot's mbarrier) NS candidates before the visit; the visit
-  // waits on the barrier and reads the row with 16-byte LDS in the same lane <-> element layout as the lane loads did
-  // (same sums in the same order: bit-identical results).  No load holds registers while it is in flight (64 instead
-  // of 72 registers: one more resident CTA) and every row crosses DRAM -> SM once (the L2 prefetch of the earlier path
-  // fetched a third of them twice).
-  auto issue_row = [&](uint64_t key, int c) {                    // owner lane only
-    const int s = c & (NS - 1);
-    mbar_expect_tx(bar_a + 8 * s, row_bytes);
-    bulk_load_1d(ring_a + uint32_t(s) * uint32_t(Ring::kSlotBytes), X + int64_t(key_index(key)) * D, row_bytes, bar_a + 8 * s);
-  };
-  if (rerank) {
-#pragma unroll
-    for (int c0 = 0; c0 < NS; ++c0)
-      if (lane == c0 / E && c0 < kp && r[c0 % E] != kKeyInf) issue_row(r[c0 % E], c0);
-  }
-  auto prefetch_rows = [&](int) {};
-#else
+  const int nl = (kp + E - 1) / E;
   auto prefetch_rows = [&](int owner) {
     if (rerank && lane == owner && owner < nl) {
 #pragma unroll
@@ -1175,7 +1247,6 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
       }
     }
   };
-#endif
   prefetch_rows(0);
   for (int L = 0; L < nl; ++L) {
     prefetch_rows(L + 1);
@@ -1185,66 +1256,11 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
       const uint64_t key = shfl_u64(r[e], L);
       if (c >= kp || key == kKeyInf) { if (lane == L && c >= kp) r[e] = kKeyInf; continue; }
       const uint32_t idx = key_index(key);
-      float rank;
-      if (rerank) {
-#if FIN_RING_KB > 0
-        mbar_wait(bar_a + 8 * (c & (NS - 1)), uint32_t(c / NS) & 1u);
-        const T* xrow = reinterpret_cast<const T*>(ring + (c & (NS - 1)) * Ring::kSlotBytes);
-#else
-        const T* xrow = X + int64_t(idx) * D;
-#endif
-        float dot = 0.f, xss = 0.f, d2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < QJ; ++j) {
-          const int d = (lane + 32 * j) * 8;
-          if (d < D) {
-            float xf[8];
-#if FIN_RING_KB > 0
-            load8s<T>(xrow + d, xf);
-#else
-            load8<T>(xrow + d, xf);
-#endif
-            if (mode == MODE_L2) {                                 // warp-uniform: only the sums the metric needs
-#pragma unroll
-              for (int t = 0; t < 8; ++t) { const float df = qf[j][t] - xf[t]; d2 = fmaf(df, df, d2); }
-            } else {
-#pragma unroll
-              for (int t = 0; t < 8; ++t) { dot = fmaf(xf[t], qf[j][t], dot); xss = fmaf(xf[t], xf[t], xss); }
-            }
-          }
-        }
-        if (mode == MODE_L2) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-        } else {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            dot += __shfl_xor_sync(0xffffffffu, dot, o);
-            xss += __shfl_xor_sync(0xffffffffu, xss, o);
-          }
-        }
-#if FIN_RING_KB > 0
-        {   // every lane's reads of the slot fed the butterfly above: the slot takes candidate c + NS
-          __syncwarp();
-          const uint64_t k2 = r[(e + NS) % E];
-          if (lane == L + (e + NS) / E && c + NS < kp && k2 != kKeyInf) issue_row(k2, c + NS);
-        }
-#endif
-        if (mode == MODE_L2) rank = d2;
-        else {
-          const float xn = sqrtf(xss);
-          float cs = (qn != 0.f && xn != 0.f) ? dot / (qn * xn) : 0.f;
-          if (mode == MODE_ABSCOS) cs = fabsf(cs);
-          rank = -cs;
-        }
-      } else {
-        const float v = -key_rank(key);                          // epilogue-domain score
-        if (mode == MODE_L2) rank = fmaxf(qss - v, 0.f);         // |q|^2 + |x|^2 - 2 q.x
-        else rank = -(v * (qn != 0.f ? 1.0f / qn : 0.f));
-      }
+      const float rank = rerank ? exact_rank(X + int64_t(idx) * D, std::false_type{}, [] {}) : epilogue_rank(key);
       if (lane == L) r[e] = make_key(rank, idx);
     }
   }
+#endif
 #pragma unroll
   for (int e = 0; e < E; ++e) if (lane * E + e >= kp) r[e] = kKeyInf;
   warp_sort_shared<E>(r, lane);
