@@ -1042,8 +1042,8 @@ struct Certify {
 template <int E, typename T, int QJ>
 __global__ void __launch_bounds__(128)
 gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __restrict__ thr_g, const T* __restrict__ Q,
-                     const T* __restrict__ X, int nq, int D, int P, int kp, int k, int mode, int rerank, MetricParams mp,
-                     int64_t index_offset, Certify cert,
+                     const T* __restrict__ X, const float* __restrict__ xsq, int nq, int D, int P, int kp, int k, int mode,
+                     int rerank, MetricParams mp, int64_t index_offset, Certify cert,
                      float* __restrict__ out_score, int64_t* __restrict__ out_idx) {
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -1139,9 +1139,9 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
   const float qn = sqrtf(qss);
 
   const uint32_t row_bytes = uint32_t(D) * uint32_t(sizeof(T));
-  // exact rank value of one candidate from its row (global memory, or a ring slot in shared memory): direct fp32 sums,
-  // lane <-> element layout and butterfly identical in both builds, so the results are bit-identical
-  auto exact_rank = [&](const T* xrow, auto in_smem, auto&& after_reads) -> float {
+  // exact sums of one candidate from its row (global memory, or a ring slot in shared memory): q.x (or sum (q-x)^2 for
+  // L2) and, when asked for, |x|^2 - direct fp32 sums, lane <-> element layout and butterfly identical in every build
+  auto row_sums = [&](const T* xrow, auto in_smem, auto with_xss, float& xss_out, auto&& after_reads) -> float {
     float dot = 0.f, xss = 0.f, d2 = 0.f;
 #pragma unroll
     for (int j = 0; j < QJ; ++j) {
@@ -1154,7 +1154,10 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
           for (int t = 0; t < 8; ++t) { const float df = qf[j][t] - xf[t]; d2 = fmaf(df, df, d2); }
         } else {
 #pragma unroll
-          for (int t = 0; t < 8; ++t) { dot = fmaf(xf[t], qf[j][t], dot); xss = fmaf(xf[t], xf[t], xss); }
+          for (int t = 0; t < 8; ++t) {
+            dot = fmaf(xf[t], qf[j][t], dot);
+            if constexpr (decltype(with_xss)::value) xss = fmaf(xf[t], xf[t], xss);
+          }
         }
       }
     }
@@ -1165,11 +1168,14 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        xss += __shfl_xor_sync(0xffffffffu, xss, o);
+        if constexpr (decltype(with_xss)::value) xss += __shfl_xor_sync(0xffffffffu, xss, o);
       }
     }
     after_reads();
-    if (mode == MODE_L2) return d2;
+    xss_out = xss;
+    return mode == MODE_L2 ? d2 : dot;
+  };
+  auto cosine_rank = [&](float dot, float xss) -> float {          // geometric_metrics.py:12-18 on the exact sums
     const float xn = sqrtf(xss);
     float cs = (qn != 0.f && xn != 0.f) ? dot / (qn * xn) : 0.f;
     if (mode == MODE_ABSCOS) cs = fabsf(cs);
@@ -1208,27 +1214,49 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
 #pragma unroll
     for (int c0 = 0; c0 < NS; ++c0) issue_row(c0);
   }
+  // The visit leaves the raw sum (q.x, or the L2 sum) next to the row index; the per-candidate scalar tail - |x|, the
+  // division, the ordered key - is done once per candidate by the lane that owns it after the loop instead of by all 32
+  // lanes inside it, and |x|^2 comes from the prepared index (index_rows_kernel sums the row in the same lane layout and
+  // butterfly order, so xsq[i] IS the value the visit would compute, bit for bit): 16 FFMA, a butterfly, a square root and
+  // a division less per visit.
+  int n_done = 0;
 #pragma unroll 1
-  for (int c = 0; c < kp; ++c) {
+  for (; n_done < kp; ++n_done) {
+    const int c = n_done;
     const uint64_t key = stage[pos(c)];
     if (key == kKeyInf) break;                                     // sorted: nothing valid follows (warp-uniform)
-    float rank;
+    float v;
     if (rerank) {
       mbar_wait(bar_a + 8 * (c & (NS - 1)), uint32_t(c / NS) & 1u);
       const T* xrow = reinterpret_cast<const T*>(ring + (c & (NS - 1)) * Ring::kSlotBytes);
-      rank = exact_rank(xrow, std::true_type{}, [&] {
+      float unused;
+      v = row_sums(xrow, std::true_type{}, std::false_type{}, unused, [&] {
         __syncwarp();                                              // every lane's reads of the slot fed the butterfly:
         if (lane == 0) issue_row(c + NS);                          // the slot takes candidate c + NS
       });
     } else {
-      rank = epilogue_rank(key);
+      v = epilogue_rank(key);
     }
     __syncwarp();
-    if (lane == 0) stage[pos(c)] = make_key(rank, key_index(key));
+    if (lane == 0) stage[pos(c)] = (uint64_t(__float_as_uint(v)) << 32) | key_index(key);
   }
   __syncwarp();
+  {
+    uint32_t idx[E];
+    float v[E], xs[E];
 #pragma unroll
-  for (int e = 0; e < E; ++e) r[e] = stage[e * 32 + lane];
+    for (int e = 0; e < E; ++e) {
+      const uint64_t raw = stage[e * 32 + lane];
+      idx[e] = uint32_t(raw);
+      v[e] = __uint_as_float(uint32_t(raw >> 32));
+      xs[e] = (rerank && mode != MODE_L2 && lane * E + e < n_done) ? __ldg(xsq + idx[e]) : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float rank = (rerank && mode != MODE_L2) ? cosine_rank(v[e], xs[e]) : v[e];
+      r[e] = lane * E + e < n_done ? make_key(rank, idx[e]) : kKeyInf;
+    }
+  }
 #else
   // The candidates are visited one after the other (two 16-byte loads per lane and row, then a butterfly), i.e. one DRAM
   // latency per candidate.  Lane L owns the E keys of step L: one step ahead it asks the L2 for its E rows with one bulk
@@ -1256,7 +1284,14 @@ gemm_finalize_kernel(const uint64_t* __restrict__ partial, const uint32_t* __res
       const uint64_t key = shfl_u64(r[e], L);
       if (c >= kp || key == kKeyInf) { if (lane == L && c >= kp) r[e] = kKeyInf; continue; }
       const uint32_t idx = key_index(key);
-      const float rank = rerank ? exact_rank(X + int64_t(idx) * D, std::false_type{}, [] {}) : epilogue_rank(key);
+      float rank;
+      if (rerank) {
+        float xss;
+        const float sum = row_sums(X + int64_t(idx) * D, std::false_type{}, std::true_type{}, xss, [] {});
+        rank = mode == MODE_L2 ? sum : cosine_rank(sum, xss);
+      } else {
+        rank = epilogue_rank(key);
+      }
       if (lane == L) r[e] = make_key(rank, idx);
     }
   }
@@ -1607,7 +1642,8 @@ int run_gemm_topk(int metric, int dtype, const void* Q, int64_t nq, const void* 
       ring_bytes = 4 * size_t(wide ? FinRing<TT, 8>::kBytes : FinRing<TT, 2>::kBytes);
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ring_bytes));   // per device: set on every call
 #endif
-      kern<<<blocks, 128, ring_bytes, st>>>(a.partial, a.thr_g, Qp, Xp, int(nq), D, pl.P, pl.kp, k, mode, rerank, mp, index_offset, cert, out_score, out_idx);
+      kern<<<blocks, 128, ring_bytes, st>>>(a.partial, a.thr_g, Qp, Xp, reinterpret_cast<const float*>(index + IL.off_sqnorm), int(nq), D, pl.P, pl.kp,
+                                            k, mode, rerank, mp, index_offset, cert, out_score, out_idx);
     };
     if (f32) {
       const float* Qp = static_cast<const float*>(Q);
